@@ -1,0 +1,686 @@
+// Scaled-dot-product attention forward / backward on tcgen05 (K5, and the MAP
+// head's 1-query attention, K10).  Reference: flax.linen.MultiHeadDotProductAttention
+// as called at models/vit.py:93-98 (self-attention, no mask, no dropout) and
+// models/vit.py:176-178 (MAPHead probe attention): q is scaled by 1/sqrt(dh), softmax
+// over keys, weights times v.  Head dim is fixed at 64 (every ViT variant in
+// models/vit.py:297-300 has width/heads == 64 except "mu").
+//
+// All keys of one (image, head) fit on chip (N <= 256 here: 196/197 image tokens,
+// 64 text tokens), so scores for a 128-query tile live in TMEM as a single
+// [128 x Nk] fp32 tile and the softmax is exact (no online rescaling).
+//
+// q/k/v/o are strided views into the fused QKV GEMM output: element (b, t, h*64+j)
+// at base + b*batch_stride + t*row_stride + h*64 + j; 3-D TMA descriptors read them
+// in place (no head transpose, no padding copies; rows past N are zero-filled).
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace bv {
+namespace {
+
+constexpr int DH = 64;
+constexpr int TQ = 128;
+constexpr int TILE_BYTES = TQ * DH * 2;       // 16 KB: 128 rows x 128 B
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ============================================================================
+// forward
+// ============================================================================
+constexpr int FWD_THREADS = 320;   // warps 0-7 softmax/epilogue, 8 TMA, 9 MMA
+
+struct FwdDev {
+  int tiles;          // B * H * QT
+  int H, QT, Nq, Nk, NKP;
+  int nstage, nbuf;
+  float scale_log2;   // scale * log2(e)
+  float* lse;         // [B, H, Nq]
+};
+
+struct FwdSmem {
+  // byte offsets from the 1024-aligned base
+  int stage_bytes, kv_bytes, p_off, o_off, x_off, bar_off, total;
+};
+
+__host__ __device__ inline FwdSmem fwd_smem_layout(int NKP, int nstage) {
+  FwdSmem L;
+  L.kv_bytes = NKP * 128;
+  L.stage_bytes = TILE_BYTES + 2 * L.kv_bytes;
+  L.p_off = nstage * L.stage_bytes;
+  const int nblk = (NKP + 63) / 64;
+  L.o_off = L.p_off + nblk * TILE_BYTES;
+  L.x_off = L.o_off + TILE_BYTES;
+  L.bar_off = L.x_off + 4 * 128 * 4;
+  L.total = L.bar_off + 128 + 1024;
+  return L;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                const FwdDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const FwdSmem L = fwd_smem_layout(p.NKP, p.nstage);
+
+  const uint32_t bar = base + L.bar_off;
+  auto in_full = [&](int s) { return bar + 8u * s; };
+  auto in_empty = [&](int s) { return bar + 8u * (2 + s); };
+  auto s_full = [&](int b) { return bar + 8u * (4 + b); };
+  auto s_empty = [&](int b) { return bar + 8u * (6 + b); };
+  const uint32_t p_full = bar + 64, p_empty = bar + 72, o_full = bar + 80, o_empty = bar + 88;
+  const uint32_t tmem_slot = bar + 96;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L.bar_off + 96);
+  float* xch = reinterpret_cast<float*>(base_ptr + L.x_off);   // [max0|max1|sum0|sum1][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(in_full(s), 1); mbar_init(in_empty(s), 1);
+      mbar_init(s_full(s), 1);  mbar_init(s_empty(s), 8);
+    }
+    mbar_init(p_full, 8); mbar_init(p_empty, 1);
+    mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t O_COL = 448;
+
+  const int my_tiles = (p.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int qt = tile % p.QT;
+        const int bh = tile / p.QT;
+        const int h = bh % p.H, b = bh / p.H;
+        const int st = i % p.nstage;
+        const uint32_t ph = static_cast<uint32_t>(i / p.nstage) & 1u;
+        mbar_wait(in_empty(st), ph ^ 1u);
+        const uint32_t q_s = base + st * L.stage_bytes;
+        const uint32_t k_s = q_s + TILE_BYTES;
+        const uint32_t v_s = k_s + L.kv_bytes;
+        mbar_expect_tx(in_full(st), L.stage_bytes);
+        tma_load_3d(q_s, &tmQ, in_full(st), h * DH, qt * TQ, b);
+        tma_load_3d(k_s, &tmK, in_full(st), h * DH, 0, b);
+        tma_load_3d(v_s, &tmV, in_full(st), h * DH, 0, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, p.NKP, 0, 0);   // Q K^T : both K-major
+      const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);      // P V   : V is MN-major
+      auto issue_s = [&](int i) {
+        const int st = i % p.nstage, bf = i % p.nbuf;
+        mbar_wait(in_full(st), static_cast<uint32_t>(i / p.nstage) & 1u);
+        mbar_wait(s_empty(bf), (static_cast<uint32_t>(i / p.nbuf) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t q_s = base + st * L.stage_bytes;
+        const uint32_t k_s = q_s + TILE_BYTES;
+        const uint32_t d = tmem_base + bf * p.NKP;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          umma_bf16_ss(d, umma_smem_desc_sw128(q_s + k * 32, 16, 1024),
+                       umma_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full(bf));
+      };
+      auto issue_pv = [&](int i) {
+        const int st = i % p.nstage;
+        mbar_wait(p_full, static_cast<uint32_t>(i) & 1u);
+        mbar_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t v_s = base + st * L.stage_bytes + TILE_BYTES + L.kv_bytes;
+        const uint32_t p_s = base + L.p_off;
+        const int ksteps = p.NKP / 16;
+        for (int j = 0; j < ksteps; ++j) {
+          const uint64_t ad = umma_smem_desc_sw128(p_s + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_smem_desc_sw128(v_s + j * 2048, 8192, 1024);
+          umma_bf16_ss(tmem_base + O_COL, ad, bd, idesc_o, j > 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(p_empty);
+        umma_commit(in_empty(st));
+      };
+      const bool ahead = (p.nstage == 2);
+      if (my_tiles > 0) issue_s(0);
+      for (int i = 0; i < my_tiles; ++i) {
+        if (ahead && i + 1 < my_tiles) issue_s(i + 1);
+        issue_pv(i);
+        if (!ahead && i + 1 < my_tiles) issue_s(i + 1);
+      }
+    }
+  } else {
+    // ---------------- softmax + epilogue (8 warps) ----------------
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int tid = threadIdx.x;            // 0..255
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const int half_cols = p.NKP >> 1;       // multiple of 8
+    const int nunits = half_cols >> 3;      // <= 16
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int qt = tile % p.QT;
+      const int bh = tile / p.QT;
+      const int h = bh % p.H, b = bh / p.H;
+      const int bf = i % p.nbuf;
+      mbar_wait(s_full(bf), static_cast<uint32_t>(i / p.nbuf) & 1u);
+      tc_fence_after();
+      uint32_t sv[16][8];
+      const uint32_t s_addr = tmem_base + lane_addr + bf * p.NKP + hf * half_cols;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (u < nunits) tmem_ld_x8(s_addr + u * 8, sv[u]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(bf));
+
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (u < nunits) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = hf * half_cols + u * 8 + j;
+            float s = __uint_as_float(sv[u][j]) * p.scale_log2;
+            s = (col < p.Nk) ? s : -INFINITY;
+            sv[u][j] = __float_as_uint(s);
+            mx = fmaxf(mx, s);
+          }
+        }
+      }
+      xch[hf * 128 + row] = mx;
+      named_bar_sync(2, 256);
+      mx = fmaxf(mx, xch[(hf ^ 1) * 128 + row]);
+      float sum = 0.f;
+      mbar_wait(p_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+      const uint32_t p_s = base + L.p_off;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (u < nunits) {
+          float e[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            e[j] = exp2f(__uint_as_float(sv[u][j]) - mx);
+            sum += e[j];
+          }
+          const int c0 = hf * half_cols + u * 8;
+          const uint32_t addr = p_s + (c0 >> 6) * TILE_BYTES + row * 128 +
+                                ((static_cast<uint32_t>((c0 & 63) >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])),
+                       "r"(pack_bf16(e[4], e[5])), "r"(pack_bf16(e[6], e[7])) : "memory");
+        }
+      }
+      xch[256 + hf * 128 + row] = sum;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      named_bar_sync(2, 256);
+      sum += xch[256 + (hf ^ 1) * 128 + row];
+
+      // ---- epilogue: O / sum -> bf16 -> smem -> TMA store
+      mbar_wait(o_full, static_cast<uint32_t>(i) & 1u);
+      tc_fence_after();
+      uint32_t ov[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + hf * 32, ov);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      const float inv = 1.0f / sum;
+      if (tid == 0) tma_store_wait_read<0>();
+      named_bar_sync(2, 256);
+      const uint32_t o_s = base + L.o_off;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
+        const uint32_t addr = o_s + row * 128 + ((piece ^ sw) << 4);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(ov[g * 8 + j]) * inv;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                     "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])),
+                     "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+      }
+      const int qrow = qt * TQ + row;
+      if (hf == 0 && qrow < p.Nq && p.lse != nullptr)
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Nq + qrow] = (mx + log2f(sum)) * LN2;
+      fence_proxy_async();
+      named_bar_sync(2, 256);
+      if (tid == 0) {
+        tma_store_3d(&tmO, o_s, h * DH, qt * TQ, b);
+        tma_store_commit();
+      }
+    }
+    if (tid == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ============================================================================
+// backward
+// ============================================================================
+// One CTA per (image, head).  Queries and keys are cut into 128-wide tiles; for each
+// (key tile kt, query tile qt):
+//   S  = Q_qt K_kt^T           dP = dO_qt V_kt^T                  (TMEM, fp32)
+//   P  = exp(scale S - lse)    dS = scale * P o (dP - delta)      (registers -> smem bf16)
+//   dV_kt += P^T dO_qt         dK_kt += dS^T Q_qt      dQ_qt += dS K_kt     (TMEM)
+// delta_i = sum_j O_ij dO_ij is computed in the prologue from the O tile.
+constexpr int BWD_THREADS = 320;
+constexpr int BWD_ROWS = 256;                       // smem rows per operand (zero-filled past N)
+constexpr int OP_BYTES = BWD_ROWS * 128;            // 32 KB
+struct BwdDev {
+  int BH, H, Nq, Nk, QT, KT;
+  float scale, scale_log2;
+  const float* lse;
+};
+constexpr int BWD_P_OFF = 4 * OP_BYTES;                       // P  [128 x 128] bf16 (2 blocks)
+constexpr int BWD_DS_OFF = BWD_P_OFF + 2 * TILE_BYTES;        // dS [128 x 128]
+constexpr int BWD_STG_OFF = BWD_DS_OFF + 2 * TILE_BYTES;      // 16 KB output staging
+constexpr int BWD_STAT_OFF = BWD_STG_OFF + TILE_BYTES;        // lse2[256], delta[256]
+constexpr int BWD_BAR_OFF = BWD_STAT_OFF + 2 * BWD_ROWS * 4;
+constexpr int BWD_SMEM = BWD_BAR_OFF + 128 + 1024;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdQ,
+                const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV,
+                const BwdDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const uint32_t q_s = base, k_s = base + OP_BYTES, v_s = base + 2 * OP_BYTES, do_s = base + 3 * OP_BYTES;
+  const uint32_t p_s = base + BWD_P_OFF, ds_s = base + BWD_DS_OFF, stg_s = base + BWD_STG_OFF;
+  float* lse2_s = reinterpret_cast<float*>(base_ptr + BWD_STAT_OFF);
+  float* delta_s = lse2_s + BWD_ROWS;
+  const uint32_t bar = base + BWD_BAR_OFF;
+  const uint32_t in_full = bar, in_empty = bar + 8, o_in_full = bar + 16, stat_ready = bar + 24;
+  const uint32_t sdp_full = bar + 32, sdp_empty = bar + 40, pds_full = bar + 48, pds_empty = bar + 56;
+  const uint32_t dkv_full = bar + 64, dkv_empty = bar + 72, dq_full = bar + 80, dq_empty = bar + 88;
+  const uint32_t tmem_slot = bar + 96;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + BWD_BAR_OFF + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmdO);
+    mbar_init(in_full, 1);   mbar_init(in_empty, 1);
+    mbar_init(o_in_full, 1); mbar_init(stat_ready, 8);
+    mbar_init(sdp_full, 1);  mbar_init(sdp_empty, 8);
+    mbar_init(pds_full, 8);  mbar_init(pds_empty, 1);
+    mbar_init(dkv_full, 1);  mbar_init(dkv_empty, 8);
+    mbar_init(dq_full, 1);   mbar_init(dq_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  constexpr uint32_t S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
+
+  const int my_items = (p.BH - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int pairs = p.KT * p.QT;
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (int it = 0; it < my_items; ++it) {
+        const int bh = blockIdx.x + it * gridDim.x;
+        const int h = bh % p.H, b = bh / p.H;
+        const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+        // operands are free once every MMA of the previous item retired
+        mbar_wait(in_empty, ph ^ 1u);
+        // O goes into the P buffer, which the previous item's MMAs have also released
+        mbar_expect_tx(o_in_full, OP_BYTES);
+        tma_load_3d(p_s, &tmO, o_in_full, h * DH, 0, b);
+        mbar_expect_tx(in_full, 4 * OP_BYTES);
+        tma_load_3d(do_s, &tmdO, in_full, h * DH, 0, b);
+        tma_load_3d(q_s, &tmQ, in_full, h * DH, 0, b);
+        tma_load_3d(k_s, &tmK, in_full, h * DH, 0, b);
+        tma_load_3d(v_s, &tmV, in_full, h * DH, 0, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t id_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
+      const uint32_t id_mm = umma_idesc_bf16(128, DH, 1, 1);    // dV, dK : A^T (MN) x B (MN)
+      const uint32_t id_km = umma_idesc_bf16(128, DH, 0, 1);    // dQ     : A (K)  x B (MN)
+      uint32_t pair_cnt = 0, kt_cnt = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+        mbar_wait(in_full, ph);
+        mbar_wait(stat_ready, ph);   // the compute warps are done with O in the P buffer
+        for (int kt = 0; kt < p.KT; ++kt) {
+          for (int qt = 0; qt < p.QT; ++qt, ++pair_cnt) {
+            const uint32_t pp = pair_cnt & 1u;
+            mbar_wait(sdp_empty, pp ^ 1u);
+            tc_fence_after();
+            const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
+            const uint32_t va = v_s + kt * TILE_BYTES, da = do_s + qt * TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + S_COL, umma_smem_desc_sw128(qa + k * 32, 16, 1024),
+                           umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + DP_COL, umma_smem_desc_sw128(da + k * 32, 16, 1024),
+                           umma_smem_desc_sw128(va + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
+            umma_commit(sdp_full);
+
+            mbar_wait(pds_full, pp);
+            if (qt == 0) mbar_wait(dkv_empty, (kt_cnt & 1u) ^ 1u);
+            if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {   // contraction over 128 query rows, 16 per step
+              const uint64_t a_p = umma_smem_desc_sw128(p_s + j * 2048, TILE_BYTES, 1024);
+              const uint64_t a_ds = umma_smem_desc_sw128(ds_s + j * 2048, TILE_BYTES, 1024);
+              const uint64_t b_do = umma_smem_desc_sw128(da + j * 2048, 8192, 1024);
+              const uint64_t b_q = umma_smem_desc_sw128(qa + j * 2048, 8192, 1024);
+              const uint32_t accv = (qt > 0 || j > 0) ? 1u : 0u;
+              umma_bf16_ss(tmem_base + DV_COL, a_p, b_do, id_mm, accv);
+              umma_bf16_ss(tmem_base + DK_COL, a_ds, b_q, id_mm, accv);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {   // contraction over 128 keys
+              const uint64_t a_ds = umma_smem_desc_sw128(ds_s + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024);
+              const uint64_t b_k = umma_smem_desc_sw128(ka + j * 2048, 8192, 1024);
+              umma_bf16_ss(tmem_base + DQ_COL + qt * DH, a_ds, b_k, id_km, (kt > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(pds_empty);
+            if (qt == p.QT - 1) { umma_commit(dkv_full); ++kt_cnt; }
+          }
+        }
+        umma_commit(dq_full);
+        umma_commit(in_empty);
+      }
+    }
+  } else {
+    // ---------------- compute warps ----------------
+    const int quarter = warp & 3, hf = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int tid = threadIdx.x;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t pair_cnt = 0, kt_cnt = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int bh = blockIdx.x + it * gridDim.x;
+      const int h = bh % p.H, b = bh / p.H;
+      const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+      // ---- prologue: delta = rowsum(O o dO), lse in log2 units
+      mbar_wait(o_in_full, ph);
+      mbar_wait(in_full, ph);
+      {
+        const int r = tid;                   // 256 threads, 256 rows
+        const uint32_t rsw = static_cast<uint32_t>(r & 7);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t off = (r >> 7) * TILE_BYTES + (r & 127) * 128 + ((static_cast<uint32_t>(c) ^ rsw) << 4);
+          uint4 a, d;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(p_s + off));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(do_s + off));
+          acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x);
+          acc += bf16_lo(a.y) * bf16_lo(d.y) + bf16_hi(a.y) * bf16_hi(d.y);
+          acc += bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z);
+          acc += bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+        }
+        delta_s[r] = acc;
+        lse2_s[r] = (r < p.Nq) ? p.lse[static_cast<int64_t>(bh) * p.Nq + r] * LOG2E : INFINITY;
+      }
+      named_bar_sync(2, 256);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stat_ready);
+
+      for (int kt = 0; kt < p.KT; ++kt) {
+        for (int qt = 0; qt < p.QT; ++qt, ++pair_cnt) {
+          const uint32_t pp = pair_cnt & 1u;
+          mbar_wait(sdp_full, pp);
+          tc_fence_after();
+          const int qrow = qt * TQ + row;
+          const bool row_ok = qrow < p.Nq;
+          const float l2 = lse2_s[qrow], dl = delta_s[qrow];
+          float pe[64];
+          {
+            uint32_t t0[32], t1[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + hf * 64, t0);
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + hf * 64 + 32, t1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const int kcol = kt * TQ + hf * 64 + j;
+              const bool ok = row_ok && (kcol < p.Nk);
+              const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
+              pe[j] = ok ? exp2f(sj * p.scale_log2 - l2) : 0.f;
+            }
+          }
+          mbar_wait(pds_empty, pp ^ 1u);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t dv[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + DP_COL + hf * 64 + c * 32, dv);
+            tmem_ld_wait();
+            if (c == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(sdp_empty);
+            }
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+              const int u = c * 4 + uu;
+              uint32_t pk[4], dk[4];
+#pragma unroll
+              for (int j2 = 0; j2 < 4; ++j2) {
+                const int j = u * 8 + j2 * 2;
+                const float d0 = p.scale * pe[j] * (__uint_as_float(dv[(j & 31)]) - dl);
+                const float d1 = p.scale * pe[j + 1] * (__uint_as_float(dv[(j & 31) + 1]) - dl);
+                pk[j2] = pack_bf16(pe[j], pe[j + 1]);
+                dk[j2] = pack_bf16(pe[j] != 0.f ? d0 : 0.f, pe[j + 1] != 0.f ? d1 : 0.f);
+              }
+              const uint32_t off = hf * TILE_BYTES + row * 128 + ((static_cast<uint32_t>(u) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_s + off), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_s + off), "r"(dk[0]), "r"(dk[1]), "r"(dk[2]), "r"(dk[3]) : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pds_full);
+
+          if (qt == p.QT - 1) {
+            // ---- dV_kt, dK_kt complete: TMEM -> bf16 -> staging -> TMA store (rows = keys)
+            mbar_wait(dkv_full, kt_cnt & 1u);
+            tc_fence_after();
+            uint32_t a[32], c[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + DV_COL + hf * 32, a);
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + DK_COL + hf * 32, c);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dkv_empty);
+            ++kt_cnt;
+            for (int which = 0; which < 2; ++which) {
+              if (tid == 0) tma_store_wait_read<0>();
+              named_bar_sync(2, 256);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
+                const uint32_t addr = stg_s + row * 128 + ((piece ^ sw) << 4);
+                const uint32_t* src = which == 0 ? a : c;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 0]), __uint_as_float(src[g * 8 + 1]))),
+                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 2]), __uint_as_float(src[g * 8 + 3]))),
+                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 4]), __uint_as_float(src[g * 8 + 5]))),
+                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 6]), __uint_as_float(src[g * 8 + 7]))) : "memory");
+              }
+              fence_proxy_async();
+              named_bar_sync(2, 256);
+              if (tid == 0) {
+                tma_store_3d(which == 0 ? &tmdV : &tmdK, stg_s, h * DH, kt * TQ, b);
+                tma_store_commit();
+              }
+            }
+          }
+        }
+      }
+      // ---- dQ tiles complete
+      mbar_wait(dq_full, ph);
+      tc_fence_after();
+      for (int qt = 0; qt < p.QT; ++qt) {
+        uint32_t a[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + DQ_COL + qt * DH + hf * 32, a);
+        tmem_ld_wait();
+        if (qt == p.QT - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_empty);
+        }
+        if (tid == 0) tma_store_wait_read<0>();
+        named_bar_sync(2, 256);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
+          const uint32_t addr = stg_s + row * 128 + ((piece ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]))),
+                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]))),
+                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]))),
+                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]))) : "memory");
+        }
+        fence_proxy_async();
+        named_bar_sync(2, 256);
+        if (tid == 0) {
+          tma_store_3d(&tmdQ, stg_s, h * DH, qt * TQ, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (tid == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int make_tmap_bnd(CUtensorMap* m, const void* ptr, int cols, int64_t N, int64_t B, int64_t ld,
+                  int64_t bs, uint32_t box_rows) {
+  uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+  uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(bs) * 2};
+  uint32_t box[3] = {64, box_rows, 1};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, true);
+}
+
+int check_attn(const AttnArgs& a, const char* who) {
+  if (a.B <= 0 || a.H <= 0 || a.Nq <= 0 || a.Nk <= 0 || a.Nq > 256 || a.Nk > 256) {
+    set_error("%s: need 1 <= Nq,Nk <= 256 and B,H >= 1 (got B=%lld H=%d Nq=%d Nk=%d)", who,
+              (long long)a.B, a.H, a.Nq, a.Nk);
+    return BV_ERR_INVALID;
+  }
+  if (a.B * a.H * 2 > 0x7fffffffLL) { set_error("%s: too many (batch, head) pairs", who); return BV_ERR_INVALID; }
+  return BV_OK;
+}
+
+}  // namespace
+
+int launch_attention_fwd(const AttnArgs& a, cudaStream_t s) {
+  int rc = check_attn(a, "bv_attention_fwd");
+  if (rc) return rc;
+  FwdDev p;
+  p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
+  p.QT = (a.Nq + TQ - 1) / TQ;
+  p.NKP = (a.Nk + 15) / 16 * 16;
+  p.tiles = static_cast<int>(a.B * a.H * p.QT);
+  p.nbuf = (2 * p.NKP <= 448) ? 2 : 1;
+  p.nstage = 2;
+  FwdSmem L = fwd_smem_layout(p.NKP, 2);
+  if (L.total > 232448) { p.nstage = 1; L = fwd_smem_layout(p.NKP, 1); }
+  p.scale_log2 = a.scale * LOG2E;
+  p.lse = a.lse;
+  const int cols = a.H * DH;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, TQ))) return rc;
+  if ((rc = make_tmap_bnd(&tmK, a.k, cols, a.Nk, a.B, a.ldk, a.bsk, p.NKP))) return rc;
+  if ((rc = make_tmap_bnd(&tmV, a.v, cols, a.Nk, a.B, a.ldv, a.bsv, p.NKP))) return rc;
+  if ((rc = make_tmap_bnd(&tmO, a.o, cols, a.Nq, a.B, a.ldo, a.bso, TQ))) return rc;
+  rc = check_cuda(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       L.total), "cudaFuncSetAttribute(attn_fwd)");
+  if (rc) return rc;
+  const int sms = num_sms();
+  const int grid = p.tiles < sms ? p.tiles : sms;
+  attn_fwd_kernel<<<grid, FWD_THREADS, L.total, s>>>(tmQ, tmK, tmV, tmO, p);
+  return check_cuda(cudaGetLastError(), "attn_fwd_kernel launch");
+}
+
+int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
+  const AttnArgs& a = g.f;
+  int rc = check_attn(a, "bv_attention_bwd");
+  if (rc) return rc;
+  if (a.lse == nullptr) { set_error("bv_attention_bwd: lse required"); return BV_ERR_INVALID; }
+  BwdDev p;
+  p.BH = static_cast<int>(a.B * a.H);
+  p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
+  p.QT = (a.Nq + TQ - 1) / TQ;
+  p.KT = (a.Nk + TQ - 1) / TQ;
+  p.scale = a.scale;
+  p.scale_log2 = a.scale * LOG2E;
+  p.lse = a.lse;
+  const int cols = a.H * DH;
+  CUtensorMap tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV;
+  if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, BWD_ROWS))) return rc;
+  if ((rc = make_tmap_bnd(&tmK, a.k, cols, a.Nk, a.B, a.ldk, a.bsk, BWD_ROWS))) return rc;
+  if ((rc = make_tmap_bnd(&tmV, a.v, cols, a.Nk, a.B, a.ldv, a.bsv, BWD_ROWS))) return rc;
+  if ((rc = make_tmap_bnd(&tmO, a.o, cols, a.Nq, a.B, a.ldo, a.bso, BWD_ROWS))) return rc;
+  if ((rc = make_tmap_bnd(&tmdO, g.d_o, cols, a.Nq, a.B, g.lddo, g.bsdo, BWD_ROWS))) return rc;
+  if ((rc = make_tmap_bnd(&tmdQ, g.dq, cols, a.Nq, a.B, g.lddq, g.bsdq, TQ))) return rc;
+  if ((rc = make_tmap_bnd(&tmdK, g.dk, cols, a.Nk, a.B, g.lddk, g.bsdk, TQ))) return rc;
+  if ((rc = make_tmap_bnd(&tmdV, g.dv, cols, a.Nk, a.B, g.lddv, g.bsdv, TQ))) return rc;
+  rc = check_cuda(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       BWD_SMEM), "cudaFuncSetAttribute(attn_bwd)");
+  if (rc) return rc;
+  const int sms = num_sms();
+  const int grid = p.BH < sms ? p.BH : sms;
+  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV, p);
+  return check_cuda(cudaGetLastError(), "attn_bwd_kernel launch");
+}
+
+}  // namespace bv

@@ -1,0 +1,156 @@
+// Loss kernels.
+//  * SigLIP pairwise sigmoid loss (K14): trainers/proj/image_text/siglip.py:291-306,
+//    explicit per-device form trainers/proj/image_text/_deprecated_contrastive.py:117-141.
+//      x_ij   = (zimg_i . ztxt_j) * exp(t') + b
+//      loglik = log_sigmoid(+x_ij) on the positive diagonal, log_sigmoid(-x_ij) elsewhere
+//      loss   = (1/B) sum_i sum_j -loglik_ij            (B = GLOBAL batch, siglip.py:306)
+//    The dot products come from the tcgen05 GEMM; this kernel fuses scale+bias, the
+//    loss reduction and d loss/d dot (written as the bf16 operand of the two gradient
+//    GEMMs) plus the scalar gradients of t' and b in one pass over the [n, B] slab.
+//  * sigmoid_xent / softmax_xent (K15): utils.py:236-243, 276-281.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace bv {
+namespace {
+
+__device__ __forceinline__ float log_sigmoid(float y) {
+  // log sigma(y) = min(y, 0) - log1p(exp(-|y|))   (stable; matches jax.nn.log_sigmoid)
+  return fminf(y, 0.f) - log1pf(__expf(-fabsf(y)));
+}
+__device__ __forceinline__ float sigmoid(float y) { return 1.f / (1.f + __expf(-y)); }
+
+__device__ __forceinline__ void block_reduce3(float& a, float& b, float& c, float* sh) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) { sh[warp] = a; sh[32 + warp] = b; sh[64 + warp] = c; }
+  __syncthreads();
+  if (warp == 0) {
+    a = lane < nw ? sh[lane] : 0.f;
+    b = lane < nw ? sh[32 + lane] : 0.f;
+    c = lane < nw ? sh[64 + lane] : 0.f;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+siglip_loss_kernel(const float* __restrict__ dots, int64_t n, int64_t B, int64_t ld,
+                   int64_t row_offset, const float* __restrict__ t_param,
+                   const float* __restrict__ b_param, float inv_B, bf16* __restrict__ G,
+                   int64_t ldg, float* __restrict__ loss, float* __restrict__ dt,
+                   float* __restrict__ db) {
+  __shared__ float sh[96];
+  const float t = __expf(t_param[0]);
+  const float bias = b_param ? b_param[0] : 0.f;
+  float l_acc = 0.f, t_acc = 0.f, b_acc = 0.f;
+  const int64_t groups = B / 4;
+  const int64_t total = n * groups;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t i = idx / groups;
+    const int64_t j0 = (idx % groups) * 4;
+    const float4 dv = *reinterpret_cast<const float4*>(dots + i * ld + j0);
+    const float d[4] = {dv.x, dv.y, dv.z, dv.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float sgn = (j0 + e == row_offset + i) ? 1.f : -1.f;
+      const float x = d[e] * t + bias;
+      l_acc -= log_sigmoid(sgn * x);
+      const float gx = -sgn * sigmoid(-sgn * x) * inv_B;    // d loss / d x
+      b_acc += gx;
+      t_acc += gx * d[e] * t;                                // d x / d t' = dot * exp(t')
+      g[e] = gx * t;                                         // d loss / d dot
+    }
+    uint2 q;
+    q.x = pack_bf16(g[0], g[1]);
+    q.y = pack_bf16(g[2], g[3]);
+    *reinterpret_cast<uint2*>(G + i * ldg + j0) = q;
+  }
+  l_acc *= inv_B;
+  block_reduce3(l_acc, t_acc, b_acc, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(loss, l_acc);
+    if (dt) atomicAdd(dt, t_acc);
+    if (db) atomicAdd(db, b_acc);
+  }
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256)
+sigmoid_xent_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                    float* __restrict__ loss, float* __restrict__ dlogits, int64_t n, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float inv_n = 1.f / static_cast<float>(n);
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float x = logits[row * C + c], y = labels[row * C + c];
+    acc -= y * log_sigmoid(x) + (1.f - y) * log_sigmoid(-x);
+    if (dlogits) dlogits[row * C + c] = (sigmoid(x) - y) * inv_n;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) atomicAdd(loss, acc * inv_n);
+}
+
+__global__ void __launch_bounds__(256)
+softmax_xent_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                    float* __restrict__ loss, float* __restrict__ dlogits, int64_t n, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float inv_n = 1.f / static_cast<float>(n);
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, logits[row * C + c]);
+  mx = warp_max(mx);
+  float se = 0.f, sy = 0.f, sxy = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float x = logits[row * C + c] - mx, y = labels[row * C + c];
+    se += __expf(x); sy += y; sxy += y * x;
+  }
+  se = warp_sum(se); sy = warp_sum(sy); sxy = warp_sum(sxy);
+  const float lse = logf(se);
+  // -sum y (x - lse) = lse * sum(y) - sum(y x)
+  if (lane == 0) atomicAdd(loss, (lse * sy - sxy) * inv_n);
+  if (dlogits) {
+    for (int c = lane; c < C; c += 32) {
+      const float x = logits[row * C + c] - mx, y = labels[row * C + c];
+      dlogits[row * C + c] = (__expf(x - lse) * sy - y) * inv_n;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_siglip_loss_ew(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
+                          const float* t_param, const float* b_param, int64_t global_B, void* G,
+                          int64_t ldg, float* loss, float* dt, float* db, cudaStream_t s) {
+  if (n <= 0 || B <= 0 || B % 4 || ld % 4 || ldg % 4 || global_B <= 0) {
+    set_error("bv_siglip_loss: need n,B > 0 and B, ld, ldg multiples of 4");
+    return BV_ERR_INVALID;
+  }
+  int64_t blocks = (n * (B / 4) + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  siglip_loss_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      dots, n, B, ld, row_offset, t_param, b_param, 1.0f / static_cast<float>(global_B),
+      reinterpret_cast<bf16*>(G), ldg, loss, dt, db);
+  return check_cuda(cudaGetLastError(), "siglip_loss_kernel launch");
+}
+
+int launch_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
+                        int64_t n, int C, cudaStream_t s) {
+  if (n <= 0) return BV_OK;
+  sigmoid_xent_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(logits, labels, loss, dlogits, n, C);
+  return check_cuda(cudaGetLastError(), "sigmoid_xent_kernel launch");
+}
+int launch_softmax_xent(const float* logits, const float* labels, float* loss, float* dlogits,
+                        int64_t n, int C, cudaStream_t s) {
+  if (n <= 0) return BV_OK;
+  softmax_xent_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(logits, labels, loss, dlogits, n, C);
+  return check_cuda(cudaGetLastError(), "softmax_xent_kernel launch");
+}
+
+}  // namespace bv

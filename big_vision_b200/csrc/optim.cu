@@ -1,0 +1,144 @@
+// Fused optimizer step over a flat parameter buffer.  Reference chain
+// (optax.py:143-149): clip_by_global_norm -> scale_by_adam(b1,b2,eps,mu_dtype) ->
+// scale(lr) -> add_decayed_weights(wd, mask) -> scale_by_schedule -> scale(-1),
+// followed by optax.apply_updates (trainers/proj/image_text/siglip.py:312-313).
+// One launch per (wd, lr-mult) parameter group updates fp32 master weights, both Adam
+// moments, and the bf16 shadow copy the GEMMs read; it also accumulates the
+// l2_params / l2_updates measurements (siglip.py:315-321).  HBM-bound:
+// 4+4 (p) + 4 (g) + 2x(2|4) (mu) + 4+4 (nu) + 2 (bf16 shadow) bytes per element.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace bv {
+namespace {
+
+__device__ __forceinline__ void block_reduce2(float& a, float& b, float* sh) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) { sh[warp] = a; sh[32 + warp] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    a = lane < nw ? sh[lane] : 0.f;
+    b = lane < nw ? sh[32 + lane] : 0.f;
+    a = warp_sum(a); b = warp_sum(b);
+  }
+}
+
+template <bool MU_BF16>
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, void* __restrict__ mu,
+            float* __restrict__ nu, bf16* __restrict__ p16, int64_t n, float lr, float b1,
+            float b2, float eps, float wd, float bc1, float bc2, const float* __restrict__ gnorm_sq,
+            float clip_norm, float grad_mult, float* __restrict__ upd_sq,
+            float* __restrict__ param_sq) {
+  __shared__ float sh[64];
+  float gscale = grad_mult;
+  if (clip_norm > 0.f && gnorm_sq != nullptr) {
+    // optax.clip_by_global_norm: g if ||g|| < c else g / ||g|| * c
+    const float gn = sqrtf(gnorm_sq[0]) * grad_mult;
+    if (!(gn < clip_norm)) gscale *= clip_norm / gn;
+  }
+  float us = 0.f, ps = 0.f;
+  const int64_t n4 = n / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 nv = reinterpret_cast<float4*>(nu)[i];
+    float m[4];
+    if (MU_BF16) {
+      const uint2 q = reinterpret_cast<const uint2*>(mu)[i];
+      m[0] = bf16_lo(q.x); m[1] = bf16_hi(q.x); m[2] = bf16_lo(q.y); m[3] = bf16_hi(q.y);
+    } else {
+      const float4 q = reinterpret_cast<const float4*>(mu)[i];
+      m[0] = q.x; m[1] = q.y; m[2] = q.z; m[3] = q.w;
+    }
+    float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+    float vv[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = gg[e] * gscale;
+      m[e] = b1 * m[e] + (1.f - b1) * gr;
+      vv[e] = b2 * vv[e] + (1.f - b2) * gr * gr;
+      const float dir = (m[e] / bc1) / (sqrtf(vv[e] / bc2) + eps);
+      const float upd = -(lr * dir + wd * pp[e]);
+      pp[e] += upd;
+      us += upd * upd;
+      ps += pp[e] * pp[e];
+      if (MU_BF16) m[e] = round_bf16(m[e]);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(nu)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (MU_BF16) {
+      uint2 q; q.x = pack_bf16(m[0], m[1]); q.y = pack_bf16(m[2], m[3]);
+      reinterpret_cast<uint2*>(mu)[i] = q;
+    } else {
+      reinterpret_cast<float4*>(mu)[i] = make_float4(m[0], m[1], m[2], m[3]);
+    }
+    if (p16 != nullptr) {
+      uint2 q; q.x = pack_bf16(pp[0], pp[1]); q.y = pack_bf16(pp[2], pp[3]);
+      reinterpret_cast<uint2*>(p16)[i] = q;
+    }
+  }
+  block_reduce2(us, ps, sh);
+  if (threadIdx.x == 0) {
+    if (upd_sq) atomicAdd(upd_sq, us);
+    if (param_sq) atomicAdd(param_sq, ps);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  __shared__ float sh[64];
+  float a = 0.f, b = 0.f;
+  const int64_t n4 = n / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    a += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = x[n4 * 4 + threadIdx.x]; a += v * v; }
+  block_reduce2(a, b, sh);
+  if (threadIdx.x == 0) atomicAdd(out, a);
+}
+
+}  // namespace
+
+int launch_adam(const AdamArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return BV_OK;
+  if (a.n % 4 != 0 || (reinterpret_cast<uintptr_t>(a.params) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.grads) & 15)) {
+    set_error("bv_adam_step: group size must be a multiple of 4 elements and 16B aligned");
+    return BV_ERR_INVALID;
+  }
+  if (a.step < 1) { set_error("bv_adam_step: step is 1-based"); return BV_ERR_INVALID; }
+  const float bc1 = 1.f - powf(a.b1, static_cast<float>(a.step));
+  const float bc2 = 1.f - powf(a.b2, static_cast<float>(a.step));
+  int64_t blocks = (a.n / 4 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (a.mu_dtype == DT_BF16) {
+    adam_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+        a.params, a.grads, a.mu, a.nu, reinterpret_cast<bf16*>(a.params_bf16), a.n, a.lr, a.b1,
+        a.b2, a.eps, a.wd, bc1, bc2, a.gnorm_sq, a.clip_norm, a.grad_scale_host, a.upd_sq, a.param_sq);
+  } else {
+    adam_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+        a.params, a.grads, a.mu, a.nu, reinterpret_cast<bf16*>(a.params_bf16), a.n, a.lr, a.b1,
+        a.b2, a.eps, a.wd, bc1, bc2, a.gnorm_sq, a.clip_norm, a.grad_scale_host, a.upd_sq, a.param_sq);
+  }
+  return check_cuda(cudaGetLastError(), "adam_kernel launch");
+}
+
+int launch_sumsq(const float* x, float* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return BV_OK;
+  int64_t blocks = (n / 4 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, out, n);
+  return check_cuda(cudaGetLastError(), "sumsq_kernel launch");
+}
+
+}  // namespace bv

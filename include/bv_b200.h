@@ -1,0 +1,195 @@
+/* bv_b200.h -- C ABI of libbv_b200.so: the B200-native (sm_100a) kernels for the
+ * big_vision ViT / MLP-Mixer / SigLIP training hot path.
+ *
+ * The reference (google-research/big_vision) has no operator/FFI ABI of its own: the
+ * arithmetic below is issued through flax.linen / jax.nn call sites inside jitted
+ * Python.  Each entry point therefore cites the reference call
+ * site(s) whose computation it replaces; INTEGRATION.md shows the jax.ffi / ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all
+ *    buffers (inputs, outputs, saved-for-backward, workspace);
+ *  - functions only ENQUEUE work on `stream` (a cudaStream_t passed as void*); they
+ *    never allocate device memory and never synchronise;
+ *  - return 0 on success, a negative BV_ERR_* code otherwise; bv_last_error_string()
+ *    (thread-local) describes the last failure;
+ *  - dtype codes: BV_F32 = 0, BV_BF16 = 1.  Matrix operands of the tensor-core paths
+ *    are bf16 with fp32 accumulation; statistics, losses, parameters and parameter
+ *    gradients are fp32;
+ *  - "ld*" are row strides in ELEMENTS.  TMA operands need 16-byte aligned bases and
+ *    row strides that are multiples of 8 bf16 / 4 fp32 elements.
+ */
+#ifndef BV_B200_H_
+#define BV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BV_OK 0
+#define BV_ERR_INVALID (-1)
+#define BV_ERR_CUDA (-2)
+#define BV_ERR_UNSUPPORTED (-3)
+
+#define BV_F32 0
+#define BV_BF16 1
+
+/* GEMM epilogues */
+#define BV_EPI_NONE 0        /* D = alpha*acc                                        */
+#define BV_EPI_BIAS 1        /* D = alpha*acc + bias[n]                              */
+#define BV_EPI_BIAS_GELU 2   /* D2 = bf16(alpha*acc + bias); D = gelu_tanh(D2)       */
+#define BV_EPI_BIAS_RESID 3  /* D = bf16(alpha*acc + bias) + aux[m (% aux_row_mod), n] */
+#define BV_EPI_DGELU 4       /* D = alpha*acc * gelu_tanh'(aux[m, n])                */
+
+const char* bv_last_error_string(void);
+int bv_version(void);
+/* 1 if the library was compiled for sm_100a and a device of compute capability 10.x is
+ * current; the product path refuses to run otherwise (no CPU / other-arch fallback). */
+int bv_device_supported(void);
+
+/* ---------------------------------------------------------------------------------
+ * Dense contraction  D[M,N] = epilogue(alpha * sum_k A(m,k) B(n,k))   (tcgen05 + TMA)
+ * Replaces flax nn.Dense / nn.DenseGeneral / nn.Conv(patch,stride=patch) forward and both
+ * backward contractions: models/vit.py:72,77 (MlpBlock), :93-98 and :176-178
+ * (q/k/v/out projections inside MultiHeadDotProductAttention), :212-214 (patch embed as
+ * im2col GEMM), :261,272 (pre_logits, head); models/mlp_mixer.py:35-37,72,82;
+ * models/proj/image_text/text_transformer.py:98; the logits product
+ * trainers/proj/image_text/siglip.py:291.
+ *   a_mn / b_mn : 0 = operand stored K-major  ([M or N rows, K contiguous]),
+ *                 1 = operand stored MN-major ([K rows, M or N contiguous]).
+ *     forward  Y = X W    : A=X (a_mn=0), B=W[K,N] (b_mn=1)
+ *     dgrad    dX = dY W^T: A=dY (a_mn=0), B=W[K,N] read as [N'=K rows, K'=N] (b_mn=0)
+ *     wgrad    dW = X^T dY: A=X (a_mn=1), B=dY (b_mn=1), out fp32, reduce_out=1
+ *   reduce_out : 1 = accumulate into D with TMA reduce-add (split-K / grad accumulation)
+ *   splits     : 0 = auto, >1 only with reduce_out
+ *   block_n    : 0 = auto, else 128 or 256
+ *   bias (fp32 [N]) and aux (bf16) must be readable up to round_up(N, 8) columns.
+ * --------------------------------------------------------------------------------- */
+typedef struct bv_gemm_args {
+  const void* A; const void* B; void* D; void* D2;
+  const float* bias; const void* aux;
+  int64_t M, N, K;
+  int64_t lda, ldb, ldd, ldd2, ldaux;
+  int32_t a_mn, b_mn;
+  int32_t epilogue, out_dtype, reduce_out, splits, block_n, aux_row_mod;
+  float alpha;
+} bv_gemm_args;
+int bv_gemm(const bv_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * LayerNorm (flax nn.LayerNorm, eps=1e-6, fast variance; models/vit.py:92,103,160,181,
+ * models/mlp_mixer.py:48,53,79).  x,y: [rows,d], d % 8 == 0, d <= 2048.
+ * bwd: dx = dres + LN'(dy); dscale/dbias/dx_colsum are ACCUMULATED (atomics); any of
+ * dres, dscale, dbias, dx_colsum may be NULL.  dres has dtype dx_dtype.
+ * --------------------------------------------------------------------------------- */
+int bv_layernorm_fwd(const void* x, int x_dtype, const float* scale, const float* bias, void* y,
+                     int y_dtype, float* mean, float* rstd, int64_t rows, int32_t d, float eps,
+                     void* stream);
+int bv_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* scale,
+                     const float* mean, const float* rstd, const void* dres, void* dx,
+                     int dx_dtype, float* dscale, float* dbias, float* dx_colsum, int64_t rows,
+                     int32_t d, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Scaled-dot-product attention, head dim 64, no mask, Nq,Nk <= 256
+ * (flax MultiHeadDotProductAttention core: models/vit.py:93-98, :176-178).
+ * q/k/v/o are bf16 strided views: element (b, t, h*64 + j) at
+ * base + b*bs + t*ld + h*64 + j  (e.g. column slices of the fused QKV GEMM output).
+ * lse [B,H,Nq] fp32 = log sum_j exp(scale * q_i.k_j) is saved for the backward.
+ * --------------------------------------------------------------------------------- */
+typedef struct bv_attn_args {
+  const void* q; const void* k; const void* v; void* o; float* lse;
+  int64_t B; int32_t H, Nq, Nk;
+  int64_t ldq, ldk, ldv, ldo;
+  int64_t bsq, bsk, bsv, bso;
+  float scale;
+} bv_attn_args;
+int bv_attention_fwd(const bv_attn_args* args, void* stream);
+typedef struct bv_attn_bwd_args {
+  bv_attn_args fwd;            /* same q,k,v,o,lse as the forward call */
+  const void* d_o; int64_t lddo, bsdo;
+  void* dq; void* dk; void* dv;
+  int64_t lddq, lddk, lddv, bsdq, bsdk, bsdv;
+} bv_attn_bwd_args;
+int bv_attention_bwd(const bv_attn_bwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Data movement / small reductions
+ * --------------------------------------------------------------------------------- */
+/* image [n,H,W,C] fp32 NHWC -> bf16 patches [n*(H/P)*(W/P), round_up(P*P*C,8)], column order
+ * (ph,pw,c) = row-major HWIO conv kernel (models/vit.py:212-217). */
+int bv_patchify(const float* image, void* patches, int64_t n, int32_t H, int32_t W, int32_t C,
+                int32_t P, void* stream);
+/* out[b,l,:] = table[ids[b,l],:] + pos[l,:] (text_transformer.py:63-70); pos may be NULL */
+int bv_embed_fwd(const int32_t* ids, const float* table, const float* pos, void* out,
+                 int out_dtype, int64_t n, int32_t L, int32_t d, int32_t vocab, void* stream);
+/* dtable[ids] += dy (atomics), dpos[l] += sum_b dy; either may be NULL */
+int bv_embed_bwd(const int32_t* ids, const void* dy, int dy_dtype, float* dtable, float* dpos,
+                 int64_t n, int32_t L, int32_t d, int32_t vocab, void* stream);
+/* out[c] += sum_r x[r,c] : bias gradients */
+int bv_colsum(const void* x, int x_dtype, float* out, int64_t rows, int64_t cols, int64_t ld,
+              void* stream);
+int bv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* z = x / (||x||_2 + eps) (two_towers.py:60-61,73-74) */
+int bv_l2norm_fwd(const void* x, int x_dtype, float* z, float* norm, int64_t n, int32_t d,
+                  float eps, void* stream);
+int bv_l2norm_bwd(const float* dz, const float* z, const float* norm, void* dx, int dx_dtype,
+                  int64_t n, int32_t d, float eps, void* stream);
+/* mode 0: mean over tokens (gap); mode 1: take token `tok` (models/vit.py:245-253) */
+int bv_pool_fwd(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, int32_t N, int32_t d,
+                int32_t mode, int32_t tok, void* stream);
+int bv_pool_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int64_t n, int32_t N,
+                int32_t d, int32_t mode, int32_t tok, void* stream);
+/* y[r,:] = x[0,:] (+ row[:]) for r < rows : broadcast one row (MAP probe, models/vit.py:174) */
+int bv_broadcast_row(const void* x, int x_dtype, const float* row, void* y, int y_dtype,
+                     int64_t rows, int32_t d, void* stream);
+int bv_tanh_fwd(const void* x, void* y, int dtype, int64_t n, void* stream);
+int bv_tanh_bwd(const void* dy, const void* y, void* dx, int dtype, int64_t n, void* stream);
+int bv_gelu_fwd(const void* x, void* y, int dtype, int64_t n, void* stream);
+int bv_axpby(const void* x, const void* y, void* out, int dtype, float a, float b, int64_t n,
+             void* stream);
+/* bf16 [n,N,d] -> [n,d,round_up(N,8)] (zero pad): Mixer token mixing, mlp_mixer.py:49-51 */
+int bv_transpose_tokens(const void* x, void* y, int64_t n, int32_t N, int32_t d, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Losses
+ * --------------------------------------------------------------------------------- */
+/* SigLIP pairwise sigmoid loss on a slab of dot products dots[n,B] = zimg_local . ztxt_all^T
+ * (trainers/proj/image_text/siglip.py:291-306; per-device form
+ * _deprecated_contrastive.py:117-141).  row_offset = rank*n locates the positives.
+ * Accumulates: loss += sum_ij -loglik_ij / global_B ; dt += dloss/dt' ; db += dloss/db.
+ * Writes G[n,B] (bf16) = dloss/ddots. */
+int bv_siglip_loss(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
+                   const float* t_param, const float* b_param, int64_t global_B, void* G,
+                   int64_t ldg, float* loss, float* dt, float* db, void* stream);
+/* utils.py:236-243 / 276-281 : mean over n rows; loss is accumulated; dlogits may be NULL */
+int bv_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
+                    int64_t n, int32_t C, void* stream);
+int bv_softmax_xent(const float* logits, const float* labels, float* loss, float* dlogits,
+                    int64_t n, int32_t C, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Optimizer (optax.py:143-149 chain with scale_by_adam; siglip.py:312-321)
+ *   g' = g * grad_mult * clip(gnorm)           m,v Adam moments (mu bf16 or fp32)
+ *   p += -(lr_eff * mhat/(sqrt(vhat)+eps) + wd_eff * p)
+ * lr_eff / wd_eff already include the schedule value for this step.  Also writes the
+ * bf16 shadow copy (params_bf16, may be NULL) and accumulates |update|^2, |param|^2.
+ * --------------------------------------------------------------------------------- */
+typedef struct bv_adam_args {
+  float* params; const float* grads; void* mu; float* nu; void* params_bf16;
+  int64_t n; int32_t mu_dtype;
+  float lr_eff, b1, b2, eps, wd_eff, grad_mult, clip_norm;
+  const float* gnorm_sq;     /* device scalar: sum of squares of ALL grads (pre grad_mult) */
+  int64_t step;              /* 1-based */
+  float* upd_sq; float* param_sq;
+} bv_adam_args;
+int bv_adam_step(const bv_adam_args* args, void* stream);
+int bv_sumsq(const float* x, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BV_B200_H_ */
