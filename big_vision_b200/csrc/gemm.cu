@@ -258,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else if (p.epi == EPI_BIAS_RESID) {
             if (have_aux) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = round_bf16(v[i]) + a[i];
+              for (int i = 0; i < 8; ++i) v[i] = (OUT_F32 ? v[i] : round_bf16(v[i])) + a[i];
             }
           } else if (p.epi == EPI_DGELU) {
 #pragma unroll

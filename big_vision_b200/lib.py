@@ -113,6 +113,12 @@ def check(rc, what):
     raise BvError(f"{what} failed (code {rc}): {msg}")
 
 
+# kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
+LAUNCHES = [0]
+_LAUNCHES_PER_CALL = {"bv_embed_bwd": 2}
+
+
 def call(name, *args):
   lib = load()
   check(getattr(lib, name)(*args), name)
+  LAUNCHES[0] += _LAUNCHES_PER_CALL.get(name, 1)

@@ -1,0 +1,114 @@
+"""SigLIP training step -- mirror of `update_fn` in
+big_vision/trainers/proj/image_text/siglip.py:271-323, written out in its explicit
+data-parallel form (_deprecated_contrastive.py:117-141, :343):
+
+  zimg, ztxt = two_towers(images, labels)                       (local batch n)
+  ztxt_all   = all_gather(ztxt)                                 C1  [B, D]
+  loss       = (1/B) sum_i sum_j -log_sigmoid(+-(zimg_i.ztxt_j * exp(t) + b))
+  dztxt      = reduce_scatter(d loss / d ztxt_all)              C2
+  grads      = all_reduce_sum(local grads)                      C3 (+ loss, dt, db: C4)
+  params    += fused Adam step
+
+One process per GPU; collectives go through torch.distributed (NCCL over NVLink on the
+GPU box, gloo in the CPU tests).  The loss is normalised by the GLOBAL batch B
+(siglip.py:306), so per-rank partial losses/gradients are SUMMED across ranks.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from big_vision_b200 import ops
+
+
+class Dist:
+  """Thin view of the default process group (world size 1 when not initialised)."""
+
+  def __init__(self):
+    self.on = dist.is_available() and dist.is_initialized()
+    self.world = dist.get_world_size() if self.on else 1
+    self.rank = dist.get_rank() if self.on else 0
+
+  def all_gather_rows(self, x):
+    if self.world == 1:
+      return x
+    out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous())
+    return out
+
+  def reduce_scatter_rows(self, x):
+    if self.world == 1:
+      return x
+    out = torch.empty((x.shape[0] // self.world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM)
+    return out
+
+  def all_reduce_sum(self, x):
+    if self.world > 1:
+      dist.all_reduce(x, op=dist.ReduceOp.SUM)
+    return x
+
+
+def sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal):
+  """Pairwise sigmoid loss + gradients for the local image rows against ALL text rows.
+
+  scal: fp32 device tensor [>=1]; scal[0] += this rank's share of the loss.
+  dt/db are accumulated straight into the gradient slots of `t` and `b`.
+  Returns (dzimg [n,D] fp32, dztxt_local [n,D] fp32).
+  """
+  n, D = zimg.shape
+  ztxt_all = d.all_gather_rows(ztxt)                       # C1
+  B = ztxt_all.shape[0]
+  zi16 = ops.cast(zimg, torch.empty_like(zimg, dtype=torch.bfloat16))
+  zt16 = ops.cast(ztxt_all, torch.empty_like(ztxt_all, dtype=torch.bfloat16))
+  dots = ops.gemm(zi16, zt16, out_dtype=torch.float32)     # [n, B] = zimg . ztxt_all^T
+  has_b = "b" in P.offsets
+  G = ops.siglip_loss(dots, d.rank * n, P.f("t"), P.f("b") if has_b else None, B,
+                      scal[0:1], P.g("t"), P.g("b") if has_b else None)
+  dzimg = ops.gemm(G, zt16, b_mn=True, out_dtype=torch.float32)                  # G . ztxt_all
+  dztxt_all = ops.gemm(G, zi16, a_mn=True, b_mn=True, out_dtype=torch.float32)   # G^T . zimg
+  dztxt = d.reduce_scatter_rows(dztxt_all)                 # C2
+  return dzimg, dztxt
+
+
+def make_update_fn(model, tx, config=None):
+  """Returns update_fn(train_state, rng, batch) -> (train_state, measurements), the
+  signature of siglip.py:275.  train_state = {"params": FlatParams, "opt": opt_state};
+  it is updated IN PLACE (the reference donates it, siglip.py:273)."""
+  d = Dist()
+
+  def update_fn(train_state, rng, batch):
+    del rng  # dropout is 0 on this path; nothing stochastic in the step
+    P, opt = train_state["params"], train_state["opt"]
+    images, labels = batch["image"], batch["labels"]
+    P.zero_grad()
+    scal = torch.zeros(4, dtype=torch.float32, device=P.flat.device)
+    zimg, ztxt, saved = model.fwd(P, images, labels)
+    dzimg, dztxt = sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal)
+    model.bwd(P, dzimg, dztxt, saved)
+    d.all_reduce_sum(P.grad)                               # C3 (+ dt, db inside the flat buffer)
+    d.all_reduce_sum(scal)                                 # C4: loss
+    sc = tx.update(P, opt, grad_mult=1.0)
+    measurements = {
+        "training_loss": scal[0],
+        "l2_grads": sc[0].sqrt(),
+        "l2_params": sc[2].sqrt(),
+        "l2_updates": sc[1].sqrt(),
+    }
+    return train_state, measurements
+
+  return update_fn
+
+
+def loss_and_grads(model, P, images, labels):
+  """value_and_grad(loss_fn)(params) of siglip.py:287-311 without the optimizer: returns the
+  global loss (device scalar) with P.grad holding d loss / d params (summed over ranks)."""
+  d = Dist()
+  P.zero_grad()
+  scal = torch.zeros(4, dtype=torch.float32, device=P.flat.device)
+  zimg, ztxt, saved = model.fwd(P, images, labels)
+  dzimg, dztxt = sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal)
+  model.bwd(P, dzimg, dztxt, saved)
+  d.all_reduce_sum(P.grad)
+  d.all_reduce_sum(scal)
+  return scal[0], {"zimg": zimg, "ztxt": ztxt, "dzimg": dzimg, "dztxt": dztxt}

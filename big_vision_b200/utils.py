@@ -7,29 +7,36 @@ import math
 import numpy as np
 
 
-def steps(prefix, config, data_size=None, batch_size=None, total_steps=None, default=None):
-  """Gets duration named `prefix` out of `config` and converts it to steps (utils.py:1002)."""
-  suffixes = {"steps", "examples", "epochs", "percent"}
-  matches = {f"{prefix}_{s}" for s in suffixes if f"{prefix}_{s}" in config and config[f"{prefix}_{s}"] is not None}
-  if prefix in config and config[prefix] is not None:
-    matches.add(prefix)
+def steps(prefix, config, data_size=None, batch_size=None, total_steps=None, default=ValueError):
+  """Gets duration named `prefix` out of `config` and converts it to steps (utils.py:1002-1067):
+  `{prefix}_{steps,examples,epochs,percent}`, negative entries ignored, rounded to nearest
+  with a floor of one step unless zero was asked for."""
+  suffixes = ("steps", "examples", "epochs", "percent")
+  matches = set()
+  for s in suffixes:
+    x = config.get(f"{prefix}_{s}")
+    if x is not None and x >= 0:
+      matches.add(f"{prefix}_{s}")
   assert len(matches) <= 1, f"Only one of '{matches}' should be defined."
-  if not matches:
-    if default is not None:
-      return default
-    raise ValueError(f"Cannot convert {prefix} to steps, due to missing batch_size/data_size/"
-                     f"total_steps, or invalid config {dict(config)}")
-  key = matches.pop()
-  v = config[key]
-  if key == prefix or key.endswith("_steps"):
-    return int(v)
-  if key.endswith("_examples"):
-    return max(int(v / batch_size), 1) if v else 0
-  if key.endswith("_epochs"):
-    return max(int(v * data_size / batch_size), 1) if v else 0
-  if key.endswith("_percent"):
-    return max(int(v * total_steps), 1) if v else 0
-  raise ValueError(key)
+
+  if f"{prefix}_steps" in matches:
+    return config[f"{prefix}_steps"]
+
+  def to_integer(x):
+    return max(1, round(x)) if x else 0
+
+  if batch_size and f"{prefix}_examples" in matches:
+    return to_integer(config[f"{prefix}_examples"] / batch_size)
+  if batch_size and data_size and f"{prefix}_epochs" in matches:
+    return to_integer(config[f"{prefix}_epochs"] * (data_size / batch_size))
+  if total_steps and f"{prefix}_percent" in matches:
+    pct = config[f"{prefix}_percent"]
+    assert 0.0 <= pct <= 1.0, f"Percents should lie in [0.0, 1.0], but {prefix}_percent is {pct}"
+    return to_integer(pct * total_steps)
+  if default is ValueError:
+    raise ValueError(f"Cannot convert {prefix} to steps, due to missing batch_size ({batch_size}), "
+                     f"data_size ({data_size}), total_steps ({total_steps}), or config entry")
+  return default
 
 
 def create_learning_rate_schedule(total_steps, batch_size=None, data_size=None, base=1.0,

@@ -1,0 +1,313 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  Never imported by the product path (big_vision_b200/).
+
+CPU restatement of the reference's algorithm for the SigLIP / ViT / MLP-Mixer hot path, in
+torch-CPU float64 with autograd providing the reference gradients.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may use it.
+
+PARITY UNPINNED: the reference's arithmetic lives in un-vendored, un-pinned flax / jax
+(requirements.txt:7-8), neither of which is installed here or on the GPU box (probed:
+`import jax` -> ModuleNotFoundError on both), and the reference's own tests hold no golden
+vectors for this path.  What pins this file instead:
+  * every function cites the reference lines it restates;
+  * the flax-internal semantics it encodes are the documented defaults (LayerNorm eps=1e-6 with
+    fast variance, tanh-approximate gelu, q scaled by 1/sqrt(dh) before the dot, softmax over
+    keys, DenseGeneral kernel shapes) and are cross-checked in tests/test_oracle.py against
+    torch.nn.functional's independent implementations of the same operators;
+  * the global loss (siglip.py:287-306) is checked against the explicit per-device form
+    (_deprecated_contrastive.py:117-141) -- two restatements of one quantity must agree.
+
+`mm="bfloat16"` emulates the CUDA path's rounding points (bf16 matmul operands / outputs and
+a bf16 residual stream, fp32-or-better everywhere else) with straight-through gradients, so
+forward parity can be asserted tightly; `mm="float32"` is the plain high-precision model.
+"""
+import math
+
+import numpy as np
+import torch
+
+F64 = torch.float64
+
+
+# --------------------------------------------------------------------------------------------
+# numerics helpers
+# --------------------------------------------------------------------------------------------
+class _RoundBf16(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, x):
+    return x.to(torch.float32).to(torch.bfloat16).to(x.dtype)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g
+
+
+def rnd(x, mm):
+  """Round to bf16 (straight-through) when emulating the bf16 matmul path."""
+  return _RoundBf16.apply(x) if mm == "bfloat16" else x
+
+
+def gelu_tanh(x):
+  """flax.linen.gelu default (approximate=True), called at models/vit.py:75, mlp_mixer.py:36."""
+  return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+def layer_norm(x, scale, bias, eps=1e-6):
+  """flax.linen.LayerNorm defaults (models/vit.py:92,103,160,181): eps 1e-6, stats over the last
+  axis, use_fast_variance: var = max(E[x^2] - E[x]^2, 0)."""
+  mean = x.mean(-1, keepdim=True)
+  var = torch.clamp((x * x).mean(-1, keepdim=True) - mean * mean, min=0.0)
+  return (x - mean) * torch.rsqrt(var + eps) * scale + bias
+
+
+def dense(x, kernel, bias, mm):
+  """flax nn.Dense(dtype=mm): y = x @ kernel + bias, operands cast to mm, fp32 accumulate."""
+  y = rnd(x, mm) @ rnd(kernel, mm)
+  return y + bias if bias is not None else y
+
+
+def mha(xq, xkv, p, heads, mm):
+  """flax.linen.MultiHeadDotProductAttention (models/vit.py:93-98,176-178).
+  p: query/key/value {kernel [d,h,dh], bias [h,dh]}, out {kernel [h,dh,d], bias [d]}.
+  query is scaled by 1/sqrt(dh) before the dot; softmax over keys; no mask, no dropout."""
+  d = xq.shape[-1]
+  dh = d // heads
+
+  def proj(x, name):
+    k = p[name + "/kernel"].reshape(d, d)
+    b = p[name + "/bias"].reshape(d)
+    return rnd(dense(x, k, b, mm), mm)
+
+  q, k, v = proj(xq, "query"), proj(xkv, "key"), proj(xkv, "value")
+  B, Nq, Nk = xq.shape[0], xq.shape[1], xkv.shape[1]
+  q = q.reshape(B, Nq, heads, dh).transpose(1, 2)
+  k = k.reshape(B, Nk, heads, dh).transpose(1, 2)
+  v = v.reshape(B, Nk, heads, dh).transpose(1, 2)
+  s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+  w = torch.softmax(s, dim=-1)
+  if mm == "bfloat16":
+    # the kernel feeds un-normalised bf16 probabilities exp(s - max) to the tensor core and
+    # divides by their fp32 sum afterwards
+    e = torch.exp(s - s.max(-1, keepdim=True).values)
+    o = (rnd(e, mm) @ v) / e.sum(-1, keepdim=True)
+  else:
+    o = w @ v
+  o = rnd(o, mm).transpose(1, 2).reshape(B, Nq, d)
+  return dense(o, p["out/kernel"].reshape(d, d), p["out/bias"], mm)
+
+
+def sub(p, prefix):
+  """Sub-tree of a flat 'a/b/c' dict."""
+  n = len(prefix)
+  return {k[n:]: v for k, v in p.items() if k.startswith(prefix)}
+
+
+def mlp_block(x, p, mm):
+  """vit.MlpBlock (models/vit.py:57-78)."""
+  h = rnd(dense(x, p["Dense_0/kernel"], p["Dense_0/bias"], mm), mm)
+  h = rnd(gelu_tanh(h), mm)
+  return dense(h, p["Dense_1/kernel"], p["Dense_1/bias"], mm)
+
+
+def encoder_block(x, p, heads, mm):
+  """vit.Encoder1DBlock.__call__ (models/vit.py:89-112)."""
+  y = rnd(layer_norm(x, p["LayerNorm_0/scale"], p["LayerNorm_0/bias"]), mm)
+  y = rnd(mha(y, y, sub(p, "MultiHeadDotProductAttention_0/"), heads, mm), mm)
+  x = rnd(x + y, mm)
+  y = rnd(layer_norm(x, p["LayerNorm_1/scale"], p["LayerNorm_1/bias"]), mm)
+  y = rnd(mlp_block(y, sub(p, "MlpBlock_0/"), mm), mm)
+  return rnd(x + y, mm)
+
+
+def encoder(x, p, depth, heads, mm):
+  """vit.Encoder (models/vit.py:115-160), scan=False naming; returns the PRE-norm stream and
+  the encoder_norm output."""
+  for i in range(depth):
+    x = encoder_block(x, sub(p, f"encoderblock_{i}/"), heads, mm)
+  return layer_norm(x, p["encoder_norm/scale"], p["encoder_norm/bias"])
+
+
+def map_head(x, p, heads, mm):
+  """vit.MAPHead (models/vit.py:163-183)."""
+  n = x.shape[0]
+  probe = p["probe"].expand(n, -1, -1)
+  a = rnd(mha(probe, rnd(x, mm), sub(p, "MultiHeadDotProductAttention_0/"), heads, mm), mm)
+  y = rnd(layer_norm(a, p["LayerNorm_0/scale"], p["LayerNorm_0/bias"]), mm)
+  out = a + mlp_block(y, sub(p, "MlpBlock_0/"), mm)
+  return out[:, 0]
+
+
+def posemb_sincos_2d(h, w, width, temperature=10_000.0):
+  """models/vit.py:34-44."""
+  y, x = np.mgrid[:h, :w]
+  omega = np.arange(width // 4) / (width // 4 - 1)
+  omega = 1.0 / (temperature ** omega)
+  y = np.einsum("m,d->md", y.flatten(), omega)
+  x = np.einsum("m,d->md", x.flatten(), omega)
+  return np.concatenate([np.sin(x), np.cos(x), np.sin(y), np.cos(y)], axis=1)[None]
+
+
+def patch_embed(image, kernel, bias, mm):
+  """nn.Conv(width, patch, strides=patch, padding="VALID") (models/vit.py:212-214) followed by
+  the reshape of :216-217.  kernel [ph,pw,C,width] HWIO, image NHWC."""
+  ph, pw, C, width = kernel.shape
+  n, H, W, _ = image.shape
+  x = image.reshape(n, H // ph, ph, W // pw, pw, C).permute(0, 1, 3, 2, 4, 5)
+  x = x.reshape(n, (H // ph) * (W // pw), ph * pw * C)
+  return dense(x, kernel.reshape(ph * pw * C, width), bias, mm)
+
+
+def vit_forward(p, image, cfg, mm="float32"):
+  """vit._Model.__call__ (models/vit.py:206-276).  cfg: dict(depth, num_heads, pool_type,
+  posemb, rep_size, num_classes).  p: flat dict of float64 tensors with the reference names."""
+  image = image.to(F64)
+  x = rnd(patch_embed(image, p["embedding/kernel"], p["embedding/bias"], mm), mm)
+  n, N0, d = x.shape
+  if cfg.get("posemb", "learn") == "learn":
+    pe = p["pos_embedding"]
+  else:
+    ph, pw = p["embedding/kernel"].shape[:2]
+    pe = torch.from_numpy(posemb_sincos_2d(image.shape[1] // ph, image.shape[2] // pw, d)).to(F64)
+  x = rnd(x + rnd(pe, mm), mm)
+  if cfg["pool_type"] == "tok":
+    x = torch.cat([rnd(p["cls"], mm).expand(n, -1, -1), x], dim=1)
+  x = encoder(x, sub(p, "Transformer/"), cfg["depth"], cfg["num_heads"], mm)
+  if cfg["pool_type"] == "map":
+    x = map_head(x, sub(p, "MAPHead_0/"), cfg["num_heads"], mm)
+  elif cfg["pool_type"] == "gap":
+    x = rnd(x, mm).mean(1)
+  elif cfg["pool_type"] in ("0", "tok"):
+    x = x[:, 0]
+  else:
+    raise ValueError(cfg["pool_type"])
+  if cfg.get("rep_size"):
+    x = torch.tanh(dense(x, p["pre_logits/kernel"], p["pre_logits/bias"], mm))
+  if cfg.get("num_classes"):
+    x = dense(x, p["head/kernel"], p["head/bias"], mm)
+  return x
+
+
+def text_forward(p, text, cfg, mm="float32"):
+  """text_transformer._Model.__call__ (text_transformer.py:55-99); no attention mask."""
+  x = p["Embed_0/embedding"][text.long()] + p["pos_embedding"]
+  x = rnd(x, mm)
+  x = encoder(x, sub(p, "Encoder_0/"), cfg["depth"], cfg["num_heads"], mm)
+  pool = cfg.get("pool_type", "last")
+  if pool == "last":
+    x = x[:, -1, :]
+  elif pool == "first":
+    x = x[:, 0, :]
+  elif pool in ("mean", "gap"):
+    x = rnd(x, mm).mean(1)
+  else:
+    raise NotImplementedError(pool)
+  if cfg.get("num_classes"):
+    x = dense(rnd(x, mm), p["head/kernel"], p["head/bias"], mm)
+  return x
+
+
+def l2_normalize(z):
+  """two_towers.py:60-61,73-74: z / (||z||_2 + 1e-8)."""
+  return z / (torch.linalg.norm(z, dim=1, keepdim=True) + 1e-8)
+
+
+def two_towers_forward(p, image, text, cfg, mm="float32"):
+  """two_towers.Model.__call__ (two_towers.py:39-90) -> (zimg, ztxt, {"t": exp(t'), "b": b})."""
+  ztxt = l2_normalize(text_forward(sub(p, "txt/"), text, cfg["text"], mm))
+  zimg = l2_normalize(vit_forward(sub(p, "img/"), image, cfg["image"], mm))
+  return zimg, ztxt, {"t": torch.exp(p["t"]), "b": p.get("b")}
+
+
+def siglip_loss(zimg, ztxt, t, b):
+  """loss_fn of trainers/proj/image_text/siglip.py:287-308 (GLOBAL batch)."""
+  logits = zimg @ ztxt.T
+  logits = logits * t + (b if b is not None else 0.0)
+  eye = torch.eye(zimg.shape[0], dtype=logits.dtype)
+  m1_diag1 = -torch.ones_like(logits) + 2 * eye
+  loglik = torch.nn.functional.logsigmoid(m1_diag1 * logits)
+  nll = -loglik.sum(-1)
+  return nll.mean()
+
+
+def siglip_loss_per_device(zimg, ztxt, t, b, world):
+  """sigmoid_loss of _deprecated_contrastive.py:117-141 evaluated for every "device" of a
+  world-size split, then pmean-ed (:343): must equal siglip_loss on the global batch."""
+  B = zimg.shape[0]
+  n = B // world
+  total = 0.0
+  for r in range(world):
+    zi = zimg[r * n:(r + 1) * n]
+    zt_me = ztxt[r * n:(r + 1) * n]
+    zt_ot = torch.cat([ztxt[:r * n], ztxt[(r + 1) * n:]], 0)
+    bb = b if b is not None else 0.0
+    logits_me = zi @ zt_me.T * t + bb
+    logits_ot = zi @ zt_ot.T * t + bb
+    eye = torch.eye(n, dtype=zi.dtype)
+    ll_me = torch.nn.functional.logsigmoid((-torch.ones_like(logits_me) + 2 * eye) * logits_me)
+    ll_ot = torch.nn.functional.logsigmoid(-logits_ot)
+    total = total + (-ll_me.sum(-1)).mean() + (-ll_ot.sum(-1)).mean()
+  return total / world
+
+
+def sigmoid_xent(logits, labels):
+  """utils.py:236-243."""
+  log_p = torch.nn.functional.logsigmoid(logits)
+  log_not_p = torch.nn.functional.logsigmoid(-logits)
+  return (-(labels * log_p + (1.0 - labels) * log_not_p).sum(-1)).mean()
+
+
+def softmax_xent(logits, labels):
+  """utils.py:276-281."""
+  return (-(labels * torch.log_softmax(logits, -1)).sum(-1)).mean()
+
+
+def mixer_forward(p, image, cfg, mm="float32"):
+  """mlp_mixer.MlpMixer.__call__ (models/mlp_mixer.py:70-84), stoch_depth = 0."""
+  image = image.to(F64)
+  x = rnd(patch_embed(image, p["stem/kernel"], p["stem/bias"], mm), mm)
+  for i in range(cfg["num_blocks"]):
+    bp = sub(p, f"MixerBlock_{i}/")
+    y = rnd(layer_norm(x, bp["LayerNorm_0/scale"], bp["LayerNorm_0/bias"]), mm)
+    y = y.transpose(1, 2)
+    tm = sub(bp, "token_mixing/")
+    h = rnd(gelu_tanh(rnd(dense(y, tm["Dense_0/kernel"], tm["Dense_0/bias"], mm), mm)), mm)
+    y = rnd(dense(h, tm["Dense_1/kernel"], tm["Dense_1/bias"], mm), mm).transpose(1, 2)
+    x = rnd(x + y, mm)
+    y = rnd(layer_norm(x, bp["LayerNorm_1/scale"], bp["LayerNorm_1/bias"]), mm)
+    cm = sub(bp, "channel_mixing/")
+    h = rnd(gelu_tanh(rnd(dense(y, cm["Dense_0/kernel"], cm["Dense_0/bias"], mm), mm)), mm)
+    x = rnd(x + rnd(dense(h, cm["Dense_1/kernel"], cm["Dense_1/bias"], mm), mm), mm)
+  x = layer_norm(x, p["pre_head_layer_norm/scale"], p["pre_head_layer_norm/bias"])
+  x = x.mean(1)
+  if cfg.get("num_classes"):
+    x = dense(x, p["head/kernel"], p["head/bias"], mm)
+  return x
+
+
+# --------------------------------------------------------------------------------------------
+# driver helpers for the tests / smoke / cpu baseline
+# --------------------------------------------------------------------------------------------
+def to_f64_tree(np_tree, requires_grad=False):
+  return {k: torch.tensor(np.asarray(v), dtype=F64, requires_grad=requires_grad)
+          for k, v in np_tree.items()}
+
+
+def siglip_value_and_grad(np_tree, image, text, cfg, mm="float32"):
+  """jax.value_and_grad(loss_fn)(params) of siglip.py:311 on the global batch."""
+  p = to_f64_tree(np_tree, requires_grad=True)
+  zimg, ztxt, extras = two_towers_forward(p, torch.as_tensor(image), torch.as_tensor(text), cfg, mm)
+  loss = siglip_loss(zimg, ztxt, extras["t"], extras["b"])
+  loss.backward()
+  grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
+  return float(loss.detach()), grads, zimg.detach().numpy(), ztxt.detach().numpy()
+
+
+def adam_reference(p, g, m, v, step, *, lr, b1, b2, eps, wd, sched=1.0, clip=0.0, gnorm=None):
+  """optax chain of optax.py:143-149 for one tensor (numpy, float64)."""
+  if clip and gnorm is not None and not gnorm < clip:
+    g = g / gnorm * clip
+  m = b1 * m + (1 - b1) * g
+  v = b2 * v + (1 - b2) * g * g
+  mhat = m / (1 - b1 ** step)
+  vhat = v / (1 - b2 ** step)
+  upd = -sched * (lr * mhat / (np.sqrt(vhat) + eps) + wd * p)
+  return p + upd, m, v

@@ -1,0 +1,55 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/bv_b200.h declares;
+argument validation fails loudly (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from big_vision_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+  src = open(os.path.join(ROOT, "include", "bv_b200.h")).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+  return sorted(set(re.findall(r"\b(bv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+  lib = L.load()
+  names = _header_functions()
+  assert len(names) >= 25
+  for n in names:
+    assert hasattr(lib, n), f"{n} declared in include/bv_b200.h but not exported"
+
+
+def test_binding_covers_header():
+  declared = set(_header_functions()) - {"bv_last_error_string"}
+  assert declared == set(L.SIGNATURES), (declared ^ set(L.SIGNATURES))
+
+
+def test_version_and_no_gpu_support_flag():
+  lib = L.load()
+  assert lib.bv_version() == 100
+  assert lib.bv_device_supported() in (0, 1)
+
+
+def test_invalid_arguments_fail_loudly():
+  lib = L.load()
+  args = L.GemmArgs(M=0, N=8, K=8)
+  rc = lib.bv_gemm(ctypes.byref(args), None)
+  assert rc == -1
+  assert b"empty" in lib.bv_last_error_string()
+  args = L.GemmArgs(M=8, N=12, K=8)   # N % 8 != 0
+  assert lib.bv_gemm(ctypes.byref(args), None) == -1
+  with pytest.raises(L.BvError):
+    L.call("bv_layernorm_fwd", None, 1, None, None, None, 1, None, None, 4, 12, 1e-6, None)
+
+
+def test_ops_refuse_cpu_tensors():
+  import torch
+  from big_vision_b200 import ops
+  with pytest.raises(L.BvError):
+    ops.layernorm_fwd(torch.zeros(4, 64), torch.ones(64), torch.zeros(64))

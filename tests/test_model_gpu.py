@@ -1,0 +1,103 @@
+"""GPU parity of the whole SigLIP step (two towers + pairwise sigmoid loss + backward + Adam)
+through the product's public API against the oracle and the committed golden vectors."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle import bv_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "siglip_tiny.npz")
+
+
+def _relerr(a, b):
+  a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+  return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+  from big_vision_b200.models.proj.image_text import two_towers
+  z = np.load(GOLD)
+  model = two_towers.Model(**common.TINY)
+  P = model.init(0, common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, device="cuda")
+  tree = {k[len("param:"):]: z[k] for k in z.files if k.startswith("param:")}
+  P.load_tree(tree)
+  image = torch.from_numpy(z["image"]).cuda()
+  text = torch.from_numpy(z["text"]).cuda()
+  return model, P, image, text, z, tree
+
+
+def test_forward_embeddings_match_golden(tiny):
+  model, P, image, text, z, _ = tiny
+  zimg, ztxt, out = model.apply({"params": P}, image, text)
+  # against the bf16-emulating oracle: only accumulation order differs
+  assert _relerr(zimg.cpu().numpy(), z["bfloat16:zimg"]) < 1e-2
+  assert _relerr(ztxt.cpu().numpy(), z["bfloat16:ztxt"]) < 1e-2
+  # against the float64 model: bf16 matmul tolerance
+  assert _relerr(zimg.cpu().numpy(), z["float32:zimg"]) < 4e-2
+  assert _relerr(ztxt.cpu().numpy(), z["float32:ztxt"]) < 4e-2
+  assert float(out["t"]) == pytest.approx(10.0, rel=1e-6) and float(out["b"]) == -10.0
+  assert np.allclose(np.linalg.norm(zimg.cpu().numpy(), axis=1), 1.0, atol=1e-5)
+
+
+def test_loss_and_gradients_match_golden(tiny):
+  from big_vision_b200.trainers.proj.image_text import siglip
+  model, P, image, text, z, _ = tiny
+  loss, aux = siglip.loss_and_grads(model, P, image, text)
+  assert float(loss) == pytest.approx(float(z["bfloat16:loss"]), rel=2e-3)
+  assert float(loss) == pytest.approx(float(z["float32:loss"]), rel=5e-3)
+  grads = P.numpy_tree("g")
+  gn = math.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values()))
+  assert gn == pytest.approx(float(z["bfloat16:gradnorm"]), rel=3e-2)
+  worst = {}
+  for k, g in grads.items():
+    ref = z["float32:grad:" + k]
+    worst[k] = _relerr(g, ref)
+  bad = {k: v for k, v in worst.items() if v > 6e-2}
+  assert not bad, f"gradient mismatch (rel to max|ref|): {sorted(bad.items(), key=lambda kv: -kv[1])[:8]}"
+
+
+def test_loss_gradient_is_consistent_with_finite_difference(tiny):
+  """d loss / d t' and d loss / d b from the kernels vs a central difference of the kernel loss."""
+  from big_vision_b200.trainers.proj.image_text import siglip
+  model, P, image, text, _, tree = tiny
+  P.load_tree(tree)
+  siglip.loss_and_grads(model, P, image, text)
+  gt, gb = float(P.g("t")[0]), float(P.g("b")[0])
+  eps = 1e-2
+  vals = {}
+  for name in ("t", "b"):
+    for sgn in (+1, -1):
+      P.load_tree(tree)
+      P.f(name).add_(sgn * eps)
+      l, _ = siglip.loss_and_grads(model, P, image, text)
+      vals[(name, sgn)] = float(l)
+  P.load_tree(tree)
+  assert (vals[("t", 1)] - vals[("t", -1)]) / (2 * eps) == pytest.approx(gt, rel=2e-2, abs=1e-4)
+  assert (vals[("b", 1)] - vals[("b", -1)]) / (2 * eps) == pytest.approx(gb, rel=2e-2, abs=1e-4)
+
+
+def test_update_fn_decreases_loss_and_reports_measurements(tiny):
+  from big_vision_b200 import optax as bv_optax
+  from big_vision_b200.trainers.proj.image_text import siglip
+  model, P, image, text, _, tree = tiny
+  P.load_tree(tree)
+  config = dict(optax_name="scale_by_adam", optax=dict(b2=0.95, mu_dtype="bfloat16"), lr=1e-3, wd=1e-4,
+                grad_clip_norm=1.0, schedule=dict(decay_type="cosine", warmup_steps=0))
+  tx, _ = bv_optax.make(config, P, sched_kw=dict(total_steps=100, batch_size=8, data_size=1000))
+  state = {"params": P, "opt": tx.init(P)}
+  update_fn = siglip.make_update_fn(model, tx, config)
+  losses = []
+  for _ in range(8):
+    state, m = update_fn(state, None, {"image": image, "labels": text})
+    losses.append(float(m["training_loss"]))
+    assert all(math.isfinite(float(m[k])) for k in ("l2_grads", "l2_params", "l2_updates"))
+  assert losses[-1] < losses[0]
+  assert state["opt"]["count"] == 8
+  assert torch.equal(P.half.float(), P.flat.bfloat16().float())    # bf16 shadow tracks the master copy
+  P.load_tree(tree)

@@ -1,0 +1,151 @@
+"""CPU: pins the oracle.  (1) its operators against torch.nn.functional's independent
+implementations, (2) the global SigLIP loss against the explicit per-device form, (3) the
+committed golden vectors, (4) the product's parameter tree against the reference's names."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle import bv_oracle as O
+
+F64 = torch.float64
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "siglip_tiny.npz")
+
+
+def test_layer_norm_matches_torch():
+  torch.manual_seed(0)
+  x = torch.randn(5, 7, 64, dtype=F64) * 3 + 1
+  g, b = torch.randn(64, dtype=F64), torch.randn(64, dtype=F64)
+  ref = torch.nn.functional.layer_norm(x, (64,), g, b, eps=1e-6)
+  assert torch.allclose(O.layer_norm(x, g, b), ref, atol=1e-10)
+
+
+def test_gelu_matches_torch_tanh_approximation():
+  x = torch.linspace(-6, 6, 1001, dtype=F64)
+  assert torch.allclose(O.gelu_tanh(x), torch.nn.functional.gelu(x, approximate="tanh"), atol=1e-12)
+
+
+def test_mha_matches_torch_sdpa():
+  torch.manual_seed(1)
+  B, N, d, h = 2, 9, 128, 2
+  x = torch.randn(B, N, d, dtype=F64)
+  p = {f"{n}/kernel": torch.randn(d, h, d // h, dtype=F64) * 0.1 for n in ("query", "key", "value")}
+  p.update({f"{n}/bias": torch.randn(h, d // h, dtype=F64) * 0.1 for n in ("query", "key", "value")})
+  p["out/kernel"] = torch.randn(h, d // h, d, dtype=F64) * 0.1
+  p["out/bias"] = torch.randn(d, dtype=F64) * 0.1
+  got = O.mha(x, x, p, h, "float32")
+  q = (x @ p["query/kernel"].reshape(d, d) + p["query/bias"].reshape(d)).reshape(B, N, h, -1).transpose(1, 2)
+  k = (x @ p["key/kernel"].reshape(d, d) + p["key/bias"].reshape(d)).reshape(B, N, h, -1).transpose(1, 2)
+  v = (x @ p["value/kernel"].reshape(d, d) + p["value/bias"].reshape(d)).reshape(B, N, h, -1).transpose(1, 2)
+  o = torch.nn.functional.scaled_dot_product_attention(q, k, v)   # scale 1/sqrt(dh), no mask
+  ref = o.transpose(1, 2).reshape(B, N, d) @ p["out/kernel"].reshape(d, d) + p["out/bias"]
+  assert torch.allclose(got, ref, atol=1e-9)
+
+
+def test_patch_embed_matches_conv2d():
+  torch.manual_seed(2)
+  img = torch.randn(2, 32, 48, 3, dtype=F64)
+  k = torch.randn(16, 16, 3, 8, dtype=F64)
+  b = torch.randn(8, dtype=F64)
+  got = O.patch_embed(img, k, b, "float32")
+  ref = torch.nn.functional.conv2d(img.permute(0, 3, 1, 2), k.permute(3, 2, 0, 1), b, stride=16)
+  ref = ref.permute(0, 2, 3, 1).reshape(2, -1, 8)
+  assert torch.allclose(got, ref, atol=1e-9)
+
+
+def test_posemb_sincos_layout():
+  pe = O.posemb_sincos_2d(3, 5, 16)
+  assert pe.shape == (1, 15, 16)
+  # [sin x | cos x | sin y | cos y], x fastest (models/vit.py:36-43)
+  assert np.allclose(pe[0, 1, 0], math.sin(1.0)) and np.allclose(pe[0, 1, 4], math.cos(1.0))
+  assert np.allclose(pe[0, 5, 8], math.sin(1.0)) and np.allclose(pe[0, 1, 8], 0.0)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_global_loss_equals_mean_of_per_device_losses(world):
+  torch.manual_seed(3)
+  B, D = 16, 32
+  zi = O.l2_normalize(torch.randn(B, D, dtype=F64))
+  zt = O.l2_normalize(torch.randn(B, D, dtype=F64))
+  t, b = torch.tensor(10.0, dtype=F64), torch.tensor(-10.0, dtype=F64)
+  assert torch.allclose(O.siglip_loss(zi, zt, t, b), O.siglip_loss_per_device(zi, zt, t, b, world), atol=1e-12)
+
+
+def test_classification_losses_known_answers():
+  logits = torch.tensor([[0.0, 0.0], [2.0, -2.0]], dtype=F64)
+  labels = torch.tensor([[1.0, 0.0], [1.0, 0.0]], dtype=F64)
+  s = O.sigmoid_xent(logits, labels)
+  ref = (2 * math.log(2.0) + 2 * math.log1p(math.exp(-2.0))) / 2
+  assert float(s) == pytest.approx(ref, abs=1e-12)
+  sm = O.softmax_xent(logits, labels)
+  assert float(sm) == pytest.approx((math.log(2.0) + math.log1p(math.exp(-4.0))) / 2, abs=1e-12)
+
+
+def test_adam_reference_first_step_is_sign_update():
+  p, g = np.array([1.0, -2.0]), np.array([0.5, -0.25])
+  p1, m, v = O.adam_reference(p, g, 0 * p, 0 * p, 1, lr=0.1, b1=0.9, b2=0.999, eps=0.0, wd=0.0)
+  assert np.allclose(p1, p - 0.1 * np.sign(g))
+
+
+def test_golden_vectors_reproduce():
+  z = np.load(GOLD)
+  tree = {k[len("param:"):]: z[k] for k in z.files if k.startswith("param:")}
+  cfg = common.oracle_cfg(common.TINY)
+  loss, grads, zimg, ztxt = O.siglip_value_and_grad(tree, z["image"], z["text"], cfg, "float32")
+  assert loss == pytest.approx(float(z["float32:loss"]), rel=1e-9)
+  assert np.allclose(zimg, z["float32:zimg"], atol=1e-9)
+  for k in ("t", "b", "img/MAPHead_0/probe", "txt/Embed_0/embedding",
+            "img/Transformer/encoderblock_0/MultiHeadDotProductAttention_0/key/kernel"):
+    assert np.allclose(grads[k], z["float32:grad:" + k], rtol=1e-4, atol=1e-7), k
+
+
+def test_golden_inputs_follow_the_synthetic_recipe():
+  z = np.load(GOLD)
+  image, text = common.synthetic_batch(common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE,
+                                       common.TINY["text"]["vocab_size"])
+  assert np.array_equal(image, z["image"]) and np.array_equal(text, z["text"])
+  assert (text[:, -1] == 1).all() and image.min() >= -1 and image.max() <= 1
+
+
+def test_param_tree_names_and_shapes_match_reference_layout():
+  """SURVEY.md 8b param-tree contract (names feed the optimizer's regex masks)."""
+  from big_vision_b200.models.proj.image_text import two_towers
+  model = two_towers.Model(**common.TINY)
+  P = model.init(0, common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, device="cpu")
+  tree = P.tree("f")
+  d, h, m = 64, 1, 128
+  blk = "img/Transformer/encoderblock_1/"
+  expect = {
+      "img/embedding/kernel": (16, 16, 3, d), "img/embedding/bias": (d,),
+      "img/pos_embedding": (1, 16, d),
+      blk + "LayerNorm_0/scale": (d,), blk + "LayerNorm_1/bias": (d,),
+      blk + "MultiHeadDotProductAttention_0/query/kernel": (d, h, d // h),
+      blk + "MultiHeadDotProductAttention_0/value/bias": (h, d // h),
+      blk + "MultiHeadDotProductAttention_0/out/kernel": (h, d // h, d),
+      blk + "MultiHeadDotProductAttention_0/out/bias": (d,),
+      blk + "MlpBlock_0/Dense_0/kernel": (d, m), blk + "MlpBlock_0/Dense_1/bias": (d,),
+      "img/Transformer/encoder_norm/scale": (d,),
+      "img/MAPHead_0/probe": (1, 1, d),
+      "img/MAPHead_0/MultiHeadDotProductAttention_0/key/kernel": (d, h, d // h),
+      "img/MAPHead_0/LayerNorm_0/scale": (d,), "img/MAPHead_0/MlpBlock_0/Dense_0/bias": (m,),
+      "txt/Embed_0/embedding": (64, d), "txt/pos_embedding": (1, 16, d),
+      "txt/Encoder_0/encoderblock_0/MlpBlock_0/Dense_1/kernel": (m, d),
+      "txt/Encoder_0/encoder_norm/bias": (d,), "txt/head/kernel": (d, 64), "txt/head/bias": (64,),
+      "t": (1,), "b": (1,),
+  }
+  for k, shp in expect.items():
+    assert k in tree, k
+    assert tuple(tree[k].shape) == shp, (k, tuple(tree[k].shape), shp)
+  assert not any("qkv" in k or "kernel_flat" in k or "out_proj" in k for k in tree)
+  assert float(tree["t"][0]) == pytest.approx(math.log(10.0)) and float(tree["b"][0]) == -10.0
+  # decayed (".*/kernel$") parameters sit in one contiguous range at the front of the flat buffer
+  assert 0 < P.n_decay < P.total
+  off, _ = P.offsets["img/Transformer/encoder_norm/scale"]
+  assert off >= P.n_decay
+  # round trip through the reference-named tree
+  np_tree = P.numpy_tree("f")
+  P2 = model.init(1, common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, device="cpu").load_tree(np_tree)
+  assert torch.equal(P.flat, P2.flat)

@@ -1,0 +1,53 @@
+"""CPU: host logic pinned by the reference's own known-answer tables
+(big_vision/utils_test.py:228-281)."""
+import pytest
+
+from big_vision_b200 import optax as bv_optax
+from big_vision_b200 import utils as u
+
+
+@pytest.mark.parametrize("data_size,batch_size,total,cfg,expected", [
+    (1000, None, None, dict(foo_steps=3), 3),
+    (1000, 100, None, dict(foo_epochs=3), 30),
+    (None, 100, None, dict(foo_examples=300), 3),
+    (None, None, 10, dict(foo_percent=0.30), 3),
+    (1000, 100, 10, dict(foo_steps=-1, foo_epochs=-1, foo_examples=-1, foo_percent=0.30), 3),
+    (None, None, 10, dict(foo_percent=0.0), 0),
+    (1001, None, None, dict(foo_steps=3), 3),
+    (1001, 100, None, dict(foo_epochs=3), 30),
+    (None, 101, None, dict(foo_examples=300), 3),
+    (None, None, 11, dict(foo_percent=0.30), 3),
+])
+def test_steps(data_size, batch_size, total, cfg, expected):   # utils_test.py:230-256
+  assert u.steps("foo", cfg, data_size=data_size, batch_size=batch_size, total_steps=total) == expected
+  with pytest.raises(ValueError):
+    u.steps("bar", cfg, data_size=data_size, batch_size=batch_size, total_steps=total)
+  assert u.steps("bar", cfg, data_size=data_size, batch_size=batch_size, total_steps=total,
+                 default=1234) == 1234
+
+
+@pytest.mark.parametrize("decay_type,extra,step,expected", [
+    ("linear", {}, 13, .5),
+    ("polynomial", {"end": .1, "power": 2}, 13, .325),
+    ("cosine", {}, 13, .5),
+    ("rsqrt", {"timescale": 1}, 13, 0.3333333),
+    ("stair", {"steps": [10], "mults": [.5]}, 5, 1.),
+    ("stair", {"steps": [10], "mults": [.5]}, 10, .5),
+    ("rsqrt", {"timescale": 1}, 3, .6),
+    ("rsqrt", {"timescale": 1}, 20, .05),
+])
+def test_schedule(decay_type, extra, step, expected):          # utils_test.py:260-281
+  lr_fn = u.create_learning_rate_schedule(total_steps=21, batch_size=512, base=.5,
+                                          decay_type=decay_type, scale_with_batchsize=True,
+                                          warmup_steps=5, cooldown_steps=5, **extra)
+  assert lr_fn(step) == pytest.approx(expected, abs=1e-6)
+
+
+def test_make_rejects_unbuilt_configurations():
+  with pytest.raises(NotImplementedError):
+    bv_optax.make(dict(optax_name="big_vision.scale_by_adafactor", schedule={}), None,
+                  sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
+  tx, fns = bv_optax.make(dict(optax_name="scale_by_adam", optax=dict(b2=0.95), lr=1e-3, wd=1e-4,
+                               grad_clip_norm=1.0, schedule=dict(decay_type="cosine", warmup_steps=2)),
+                          None, sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
+  assert tx.b2 == 0.95 and tx.clip == 1.0 and fns[0](0) == 0.0 and fns[0](2) == pytest.approx(1.0)
