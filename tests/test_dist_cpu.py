@@ -1,0 +1,104 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic of the SigLIP loss
+(trainers/proj/image_text/siglip.py in this repo): which columns hold a rank's positives,
+all-gather order, reduce-scatter of d ztxt, SUM (not mean) of per-rank partial losses.
+
+The CUDA kernels cannot run here, so the three ops the function calls are replaced by
+oracle-backed test doubles (this is the test harness, not a product fallback: the product's
+ops refuse CPU tensors, see tests/test_abi.py)."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+  sys.path.insert(0, ROOT)
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  from big_vision_b200 import ops
+  from big_vision_b200.trainers.proj.image_text import siglip
+  from oracle import bv_oracle as O
+
+  # ---- test doubles for the three kernels used by sigmoid_loss_fwd_bwd --------------------
+  def cast(src, dst):
+    return src          # keep fp32: this test is about the sharding algebra, not bf16 rounding
+
+  def gemm(a, b, a_mn=False, b_mn=False, out_dtype=torch.float32, **kw):
+    A = a.double().T if a_mn else a.double()
+    Bm = b.double() if b_mn else b.double().T
+    return (A @ Bm).to(out_dtype)
+
+  def siglip_loss(dots, row_offset, t_param, b_param, global_b, loss, dt, db):
+    d = dots.double().requires_grad_(True)
+    t = t_param.double().requires_grad_(True)
+    b = b_param.double().requires_grad_(True)
+    n, B = d.shape
+    m = -torch.ones(n, B, dtype=torch.float64)
+    m[torch.arange(n), row_offset + torch.arange(n)] = 1
+    l = -(torch.nn.functional.logsigmoid(m * (d * t.exp() + b))).sum() / global_b
+    l.backward()
+    loss += l.detach().float()
+    dt += t.grad.float()
+    db += b.grad.float()
+    return d.grad.float()
+
+  ops.cast, ops.gemm, ops.siglip_loss = cast, gemm, siglip_loss
+
+  class FakeP:
+    offsets = {"t": 0, "b": 1}
+    _f = {"t": torch.tensor([math.log(10.0)]), "b": torch.tensor([-10.0])}
+    _g = {"t": torch.zeros(1), "b": torch.zeros(1)}
+    def f(self, k): return self._f[k]
+    def g(self, k): return self._g[k]
+
+  g = torch.Generator().manual_seed(0)
+  B, D = 12, 16
+  n = B // world
+  zi = O.l2_normalize(torch.randn(B, D, generator=g).double())
+  zt = O.l2_normalize(torch.randn(B, D, generator=g).double())
+  P = FakeP()
+  scal = torch.zeros(4)
+  dzimg, dztxt = siglip.sigmoid_loss_fwd_bwd(P, zi[rank * n:(rank + 1) * n].float(),
+                                             zt[rank * n:(rank + 1) * n].float(), siglip.Dist(), scal)
+  dist.all_reduce(scal)
+  dist.all_reduce(P.g("t"))
+  dist.all_reduce(P.g("b"))
+  # oracle on the GLOBAL batch
+  zir, ztr = zi.clone().requires_grad_(True), zt.clone().requires_grad_(True)
+  tr = torch.tensor(math.log(10.0), dtype=torch.float64, requires_grad=True)
+  br = torch.tensor(-10.0, dtype=torch.float64, requires_grad=True)
+  l = O.siglip_loss(zir, ztr, tr.exp(), br)
+  l.backward()
+  errs = {
+      "loss": abs(float(scal[0]) - float(l.detach())),
+      "dzimg": float((dzimg.double() - zir.grad[rank * n:(rank + 1) * n]).abs().max()),
+      "dztxt": float((dztxt.double() - ztr.grad[rank * n:(rank + 1) * n]).abs().max()),
+      "dt": abs(float(P.g("t")) - float(tr.grad)),
+      "db": abs(float(P.g("b")) - float(br.grad)),
+  }
+  ret[rank] = errs
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_sigmoid_loss_equals_global_loss(world):
+  port = 29500 + os.getpid() % 1000 + world
+  ctx = mp.get_context("spawn")
+  ret = ctx.Manager().dict()
+  procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+  for p in procs:
+    p.start()
+  for p in procs:
+    p.join(120)
+    assert p.exitcode == 0
+  for r in range(world):
+    errs = ret.get(r)
+    assert errs is not None, f"rank {r} returned nothing"
+    assert all(v < 2e-5 for v in errs.values()), (r, dict(errs))

@@ -54,12 +54,18 @@ def test_loss_and_gradients_match_golden(tiny):
   grads = P.numpy_tree("g")
   gn = math.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values()))
   assert gn == pytest.approx(float(z["bfloat16:gradnorm"]), rel=3e-2)
-  worst = {}
+  # per-tensor error relative to that tensor's scale, with an absolute floor tied to the largest
+  # gradient in the model: some gradients are exactly zero in exact arithmetic (key/bias: softmax
+  # is invariant to a per-query constant), so a purely relative test is meaningless for them.
+  gmax = max(float(np.abs(z["float32:grad:" + k]).max()) for k in grads)
+  bad = {}
   for k, g in grads.items():
-    ref = z["float32:grad:" + k]
-    worst[k] = _relerr(g, ref)
-  bad = {k: v for k, v in worst.items() if v > 6e-2}
-  assert not bad, f"gradient mismatch (rel to max|ref|): {sorted(bad.items(), key=lambda kv: -kv[1])[:8]}"
+    ref = z["float32:grad:" + k].astype(np.float64)
+    err = float(np.abs(g.astype(np.float64) - ref).max())
+    tol = 6e-2 * float(np.abs(ref).max()) + 2e-3 * gmax
+    if err > tol:
+      bad[k] = (err, tol)
+  assert not bad, f"gradient mismatch (abs err, tol): {sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]}"
 
 
 def test_loss_gradient_is_consistent_with_finite_difference(tiny):
