@@ -123,6 +123,17 @@ int bv_axpby(const void* x, const void* y, void* out, int dtype, float a, float 
              void* stream) {
   return launch_axpby(x, y, out, dtype, a, b, n, S(stream));
 }
+int bv_untranspose_add(const void* y, const void* res, void* out, int64_t n, int32_t N, int32_t d,
+                       void* stream) {
+  return launch_untranspose_add(y, res, out, n, N, d, S(stream));
+}
+int bv_concat_cls(const void* x, const float* cls, void* out, int64_t n, int32_t N0, int32_t d,
+                  void* stream) {
+  return launch_concat_cls(x, cls, out, n, N0, d, S(stream));
+}
+int bv_drop_cls(const void* x, void* out, int64_t n, int32_t N0, int32_t d, void* stream) {
+  return launch_drop_cls(x, out, n, N0, d, S(stream));
+}
 int bv_transpose_tokens(const void* x, void* y, int64_t n, int32_t N, int32_t d, void* stream) {
   return launch_transpose_tokens(x, y, n, N, d, S(stream));
 }

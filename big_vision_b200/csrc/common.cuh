@@ -67,6 +67,22 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 
+// MUFU-based variants for the GEMM epilogues (bf16 outputs): tanh.approx.f32 has ~2^-11
+// relative error, well inside the 2^-9 of the bf16 rounding that follows.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float t = tanh_fast(x * fmaf(k01, x * x, k0));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+  const float k0 = 0.7978845608028654f, k01 = 0.7978845608028654f * 0.044715f;
+  const float x2 = x * x;
+  const float t = tanh_fast(x * fmaf(k01, x2, k0));
+  const float du = fmaf(3.0f * k01, x2, k0);
+  return fmaf(0.5f * x * fmaf(-t, t, 1.0f), du, fmaf(0.5f, t, 0.5f));
+}
+
 // ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------

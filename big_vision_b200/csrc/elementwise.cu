@@ -310,6 +310,67 @@ __global__ void transpose_tokens_kernel(const bf16* __restrict__ x, bf16* __rest
   }
 }
 
+// out[b,0,:] = cls[:], out[b,1+t,:] = x[b,t,:]   (models/vit.py:223-225, cls prepended AFTER posemb)
+__global__ void concat_cls_kernel(const bf16* __restrict__ x, const float* __restrict__ cls,
+                                  bf16* __restrict__ out, int64_t n, int N0, int d) {
+  const int groups = d / 8;
+  const int64_t total = n * (N0 + 1) * groups;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    const int64_t row = idx / groups;
+    const int t = static_cast<int>(row % (N0 + 1));
+    const int64_t b = row / (N0 + 1);
+    uint4 q;
+    if (t == 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(cls + g * 8));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cls + g * 8) + 1);
+      q.x = pack_bf16(a.x, a.y); q.y = pack_bf16(a.z, a.w);
+      q.z = pack_bf16(c.x, c.y); q.w = pack_bf16(c.z, c.w);
+    } else {
+      q = *reinterpret_cast<const uint4*>(x + (b * N0 + (t - 1)) * d + g * 8);
+    }
+    *reinterpret_cast<uint4*>(out + row * d + g * 8) = q;
+  }
+}
+// out[b,t,:] = x[b,1+t,:]  : drops the cls row (backward of the concat for the patch rows)
+__global__ void drop_cls_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t n,
+                                int N0, int d) {
+  const int groups = d / 8;
+  const int64_t total = n * N0 * groups;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    const int64_t row = idx / groups;
+    const int t = static_cast<int>(row % N0);
+    const int64_t b = row / N0;
+    *reinterpret_cast<uint4*>(out + row * d + g * 8) =
+        *reinterpret_cast<const uint4*>(x + (b * (N0 + 1) + t + 1) * d + g * 8);
+  }
+}
+
+// out[b,t,c] = (res ? res[b,t,c] : 0) + y[b,c,t]   with y stored [n, d, Np]: inverse of
+// transpose_tokens fused with the residual add (models/mlp_mixer.py:51-52)
+__global__ void untranspose_add_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
+                                       bf16* __restrict__ out, int N, int d, int Np) {
+  __shared__ bf16 tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < d && t < N) ? y[(b * d + c) * Np + t] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < N && c < d) {
+      float v = __bfloat162float(tile[threadIdx.x][i]);
+      if (res != nullptr) v += __bfloat162float(res[(b * N + t) * d + c]);
+      out[(b * N + t) * d + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
 
 }  // namespace
@@ -426,6 +487,27 @@ int launch_transpose_tokens(const void* x, void* y, int64_t n, int N, int d, cud
                                                       reinterpret_cast<bf16*>(y), N, d, Np);
   return check_launch("transpose_tokens_kernel");
 }
-int launch_unpatchify_grad_unused() { return BV_OK; }
+int launch_untranspose_add(const void* y, const void* res, void* out, int64_t n, int N, int d,
+                           cudaStream_t s) {
+  const int Np = (N + 7) / 8 * 8;
+  dim3 grid((N + 31) / 32, (d + 31) / 32, static_cast<unsigned>(n));
+  untranspose_add_kernel<<<grid, dim3(32, 8), 0, s>>>(reinterpret_cast<const bf16*>(y),
+                                                     reinterpret_cast<const bf16*>(res),
+                                                     reinterpret_cast<bf16*>(out), N, d, Np);
+  return check_launch("untranspose_add_kernel");
+}
+int launch_concat_cls(const void* x, const float* cls, void* out, int64_t n, int N0, int d,
+                      cudaStream_t s) {
+  if (d % 8) { set_error("bv_concat_cls: d %% 8 != 0"); return BV_ERR_INVALID; }
+  concat_cls_kernel<<<grid_for(n * (N0 + 1) * (d / 8), 256, 148 * 16), 256, 0, s>>>(
+      reinterpret_cast<const bf16*>(x), cls, reinterpret_cast<bf16*>(out), n, N0, d);
+  return check_launch("concat_cls_kernel");
+}
+int launch_drop_cls(const void* x, void* out, int64_t n, int N0, int d, cudaStream_t s) {
+  if (d % 8) { set_error("bv_drop_cls: d %% 8 != 0"); return BV_ERR_INVALID; }
+  drop_cls_kernel<<<grid_for(n * N0 * (d / 8), 256, 148 * 16), 256, 0, s>>>(
+      reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), n, N0, d);
+  return check_launch("drop_cls_kernel");
+}
 
 }  // namespace bv

@@ -12,41 +12,54 @@
 // (reference call sites: flax Dense/DenseGeneral under models/vit.py:72-77,93-98,
 //  176-178,212-214,261,272; models/mlp_mixer.py:35-37,72,82).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issue,
-// warps 2..5 = epilogue (TMEM -> regs -> swizzled smem -> TMA store / reduce).
-// Two TMEM accumulators so the epilogue of tile i overlaps the mainloop of i+1.
+// CTA pair (cta_group::2): two CTAs of a cluster own one 256 x BN output tile.  Each CTA
+// TMA-loads its 128 rows of A and its BN/2 rows of B per k-block; the leader CTA issues
+// UMMA 256 x BN x 16 instructions that read both CTAs' shared memory and write each
+// CTA's 128 x BN half of the accumulator into that CTA's TMEM.  Per SM this halves the
+// shared-memory traffic of the B operand (fill + MMA read), which is what bounds the
+// single-CTA 128 x 256 tile at ~2/3 of the tensor peak.
+//
+// Roles (320 threads per CTA): warp 0 = TMA producer, warp 1 = TMEM alloc (+ MMA issue in
+// the leader), warps 2..9 = epilogue (TMEM -> regs -> swizzled smem -> TMA store / reduce).
+// Two TMEM accumulator stages so the epilogue of tile i overlaps the mainloop of i+1.
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"
+
+#include <stdlib.h>
 
 namespace bv {
 
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int OUT_BUF_BYTES = BM * 128;      // 128 rows x 128 B
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
 
-template <int BN>
+// epilogue families (template parameter)
+enum : int { EF_BIAS = 0, EF_GELU = 1, EF_RESID = 2, EF_DGELU = 3 };
+
+template <int BN, int CTAS>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CTAS;                 // rows of B this CTA loads
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;   // 512 or 256 (power of two)
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256 (power of two)
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + 2 * OUT_BUF_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
 };
 
 struct GemmDev {
   int M, N, K;
-  int num_m_tiles, num_n_tiles, total_tiles;
+  int num_m_tiles, num_n_tiles, total_tiles;   // m tiles count CTA-pair tiles when CTAS == 2
   int kblocks_total, kblocks_per_split;
   int a_mn, b_mn;        // 1 = MN-major
-  int epi;
   int reduce_out;        // 1 = TMA reduce-add into D (split-K / grad accumulation)
   float alpha;
   const float* bias;
@@ -55,12 +68,56 @@ struct GemmDev {
   int aux_row_mod;
 };
 
-template <int BN, bool OUT_F32>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+// TMA load whose completion may be signalled on the CTA-pair leader's mbarrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+
+template <int BN, bool OUT_F32, int EF, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
             const GemmDev p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -78,85 +135,110 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
-    if (p.epi == EPI_BIAS_GELU) tma_prefetch_desc(&tmD2);
+    if (EF == EF_GELU) tma_prefetch_desc(&tmD2);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), EPI_WARPS * CTAS);   // one arrive per epilogue warp of each CTA
     }
     fence_barrier_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(tmem_slot), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tile_start = (CTAS == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = (CTAS == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   auto decode_tile = [&](int tile, int& m0, int& n0, int& kb0, int& kb1) {
     int n_tile = tile % p.num_n_tiles;
     int rest = tile / p.num_n_tiles;
     int m_tile = rest % p.num_m_tiles;
     int split = rest / p.num_m_tiles;
-    m0 = m_tile * BM;
+    m0 = m_tile * (BM * CTAS) + static_cast<int>(cta_rank) * BM;   // this CTA's first row
     n0 = n_tile * BN;
     kb0 = split * p.kblocks_per_split;
     kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
   };
 
   if (warp_idx == 0) {
-    // ========================= TMA producer =========================
+    // ========================= TMA producer (every CTA) =========================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
         int m0, n0, kb0, kb1;
         decode_tile(tile, m0, n0, kb0, kb1);
+        const int nb0 = n0 + static_cast<int>(cta_rank) * C::B_ROWS;   // this CTA's slice of B
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_s = base + stage * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          // the pair leader's barrier collects the bytes of both CTAs
+          uint32_t fb = full_bar(stage);
+          if (CTAS == 2) {
+            if (leader) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+            else fb = mapa_cta(fb, 0);
+          } else {
+            mbar_expect_tx(fb, C::STAGE_BYTES);
+          }
           const int k0 = kb * BK;
           if (p.a_mn) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(a_s + j * 8192, &tmA, full_bar(stage), m0 + 64 * j, k0);
+            for (int j = 0; j < BM / 64; ++j) {
+              if (CTAS == 2) tma_load_2d_pair(a_s + j * 8192, &tmA, fb, m0 + 64 * j, k0);
+              else tma_load_2d(a_s + j * 8192, &tmA, fb, m0 + 64 * j, k0);
+            }
           } else {
-            tma_load_2d(a_s, &tmA, full_bar(stage), k0, m0);
+            if (CTAS == 2) tma_load_2d_pair(a_s, &tmA, fb, k0, m0);
+            else tma_load_2d(a_s, &tmA, fb, k0, m0);
           }
           if (p.b_mn) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_s + j * 8192, &tmB, full_bar(stage), n0 + 64 * j, k0);
+            for (int j = 0; j < C::B_ROWS / 64; ++j) {
+              if (CTAS == 2) tma_load_2d_pair(b_s + j * 8192, &tmB, fb, nb0 + 64 * j, k0);
+              else tma_load_2d(b_s + j * 8192, &tmB, fb, nb0 + 64 * j, k0);
+            }
           } else {
-            tma_load_2d(b_s, &tmB, full_bar(stage), k0, n0);
+            if (CTAS == 2) tma_load_2d_pair(b_s, &tmB, fb, k0, nb0);
+            else tma_load_2d(b_s, &tmB, fb, k0, nb0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ========================= MMA issuer =========================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    // ========================= MMA issuer (pair leader only) =========================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
         int m0, n0, kb0, kb1;
         decode_tile(tile, m0, n0, kb0, kb1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -171,28 +253,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = umma_smem_desc_sw128(a_s + k * a_kstep, a_lbo, 1024u);
             const uint64_t bdesc = umma_smem_desc_sw128(b_s + k * b_kstep, b_lbo, 1024u);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (CTAS == 2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, accf);
+            else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accf);
           }
-          umma_commit(empty_bar(stage));   // smem slot free once these MMAs retire
+          // smem slot free (in both CTAs) once these MMAs retire
+          if (CTAS == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));       // accumulator complete
+        // accumulator complete: wake the epilogue warps of both CTAs
+        if (CTAS == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ========================= epilogue =========================
+    // ========================= epilogue (8 warps, every CTA) =========================
     const int ep_tid = threadIdx.x - 64;
-    const int lane_grp = warp_idx & 3;              // TMEM lanes this warp may access
-    const int row = lane_grp * 32 + lane;           // row within the tile == TMEM lane
+    const int quarter = warp_idx & 3;               // TMEM lanes this warp may access
+    const int half = (warp_idx - 2) >> 2;           // which half of each staging chunk's columns
+    const int row = quarter * 32 + lane;            // row within this CTA's tile == TMEM lane
     const uint32_t sw = static_cast<uint32_t>(row & 7);
-    const bool dual = (p.epi == EPI_BIAS_GELU);
-    constexpr int SUB_PER_FLUSH = OUT_F32 ? 1 : 2;  // 32-col sub-chunks per 128B staging row
-    constexpr int CH = OUT_F32 ? 32 : 64;           // columns per TMA store
+    constexpr bool DUAL = (EF == EF_GELU);
+    constexpr int CH = OUT_F32 ? 32 : 64;           // columns per staging chunk / TMA store
+    constexpr int WC = CH / 2;                      // columns per warp per chunk (16 or 32)
+    constexpr int NCHUNK = BN / CH;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t flush = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const bool unit_alpha = (p.alpha == 1.0f);
+    for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
       int m0, n0, kb0, kb1;
       decode_tile(tile, m0, n0, kb0, kb1);
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -200,72 +289,83 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int grow = m0 + row;
       const bool row_ok = grow < p.M;
       const bf16* aux_row = nullptr;
-      if (p.aux != nullptr && row_ok) {
+      if ((EF == EF_RESID || EF == EF_DGELU) && row_ok) {
         long long ar = p.aux_row_mod > 0 ? (grow % p.aux_row_mod) : grow;
         aux_row = p.aux + ar * p.ldaux;
       }
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 
 #pragma unroll 1
-      for (int sc = 0; sc < BN / 32; ++sc) {
-        const int sub = sc % SUB_PER_FLUSH;
-        const uint32_t buf = dual ? out_buf : out_buf + (flush & 1u) * OUT_BUF_BYTES;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + sc * 32, r);
+      for (int c = 0; c < NCHUNK; ++c) {
+        const uint32_t buf = DUAL ? out_buf : out_buf + (flush & 1u) * OUT_BUF_BYTES;
+        const int col_t = c * CH + half * WC;       // first column (within the tile) of this warp
+        const int ncol0 = n0 + col_t;
+        uint32_t r[WC];
+        if constexpr (OUT_F32) tmem_ld_32x32b_x16(t_row + col_t, r);
+        else tmem_ld_32x32b_x32(t_row + col_t, r);
+        // issue the aux loads while the TMEM load is in flight
+        uint4 aq[WC / 8];
+        if (EF == EF_RESID || EF == EF_DGELU) {
+#pragma unroll
+          for (int g = 0; g < WC / 8; ++g) {
+            aq[g] = make_uint4(0u, 0u, 0u, 0u);
+            if (aux_row != nullptr && ncol0 + g * 8 < p.N)
+              aq[g] = *reinterpret_cast<const uint4*>(aux_row + ncol0 + g * 8);
+          }
+        }
         tmem_ld_wait();
-        if (sc == BN / 32 - 1) {
+        if (c == NCHUNK - 1) {
           // accumulator fully drained into registers -> hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        if (sub == 0) {
-          // make sure the TMA store that last used this staging buffer has read it
-          if (ep_tid == 0) {
-            if (dual) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          if (lane == 0) {
+            if (CTAS == 2 && !leader) mbar_arrive_cluster(mapa_cta(tempty_bar(acc), 0));
+            else mbar_arrive(tempty_bar(acc));
           }
-          named_bar_sync(1, EPI_THREADS);
         }
-        const int ncol0 = n0 + sc * 32;
+        // make sure the TMA store that last used this staging buffer has read it
+        if (ep_tid == 0) {
+          if (DUAL) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+        }
+        named_bar_sync(1, EPI_THREADS);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {       // 8 columns per group
+        for (int g = 0; g < WC / 8; ++g) {      // 8 columns per group
           const int nc = ncol0 + g * 8;
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
-          const bool col_ok = nc < p.N;      // N % 8 == 0
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+          if (!unit_alpha) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+          }
+          const bool col_ok = nc < p.N;
           if (p.bias != nullptr && col_ok) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4));
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
-          float a[8];
-          bool have_aux = false;
-          if (aux_row != nullptr && col_ok) {
-            const uint4 q = *reinterpret_cast<const uint4*>(aux_row + nc);
-            a[0] = bf16_lo(q.x); a[1] = bf16_hi(q.x); a[2] = bf16_lo(q.y); a[3] = bf16_hi(q.y);
-            a[4] = bf16_lo(q.z); a[5] = bf16_hi(q.z); a[6] = bf16_lo(q.w); a[7] = bf16_hi(q.w);
-            have_aux = true;
-          }
           float v2[8];
-          if (p.epi == EPI_BIAS_GELU) {
+          if (EF == EF_GELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               v2[i] = round_bf16(v[i]);
-              v[i] = gelu_tanh(v2[i]);
+              v[i] = gelu_tanh_fast(v2[i]);
             }
-          } else if (p.epi == EPI_BIAS_RESID) {
-            if (have_aux) {
+          } else if (EF == EF_RESID || EF == EF_DGELU) {
+            const uint4 q = aq[g];
+            const float a[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                                bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+            if (EF == EF_RESID) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = (OUT_F32 ? v[i] : round_bf16(v[i])) + a[i];
-            }
-          } else if (p.epi == EPI_DGELU) {
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = have_aux ? v[i] * gelu_tanh_grad(a[i]) : 0.f;
+              for (int i = 0; i < 8; ++i) v[i] *= gelu_tanh_grad_fast(a[i]);
+            }
           }
           if (OUT_F32) {
-            const uint32_t p0 = static_cast<uint32_t>(g * 2), p1 = p0 + 1;
+            const uint32_t p0 = static_cast<uint32_t>(half * 4 + g * 2), p1 = p0 + 1;
             const uint32_t a0 = buf + row * 128 + ((p0 ^ sw) << 4);
             const uint32_t a1 = buf + row * 128 + ((p1 ^ sw) << 4);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(v[0]),
@@ -273,12 +373,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(v[4]),
                          "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
           } else {
-            const uint32_t piece = static_cast<uint32_t>(sub * 4 + g);
+            const uint32_t piece = static_cast<uint32_t>(half * 4 + g);
             const uint32_t a0 = buf + row * 128 + ((piece ^ sw) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0),
                          "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
                          "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
-            if (dual) {
+            if (DUAL) {
               const uint32_t a2 = a0 + OUT_BUF_BYTES;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a2),
                            "r"(pack_bf16(v2[0], v2[1])), "r"(pack_bf16(v2[2], v2[3])),
@@ -286,37 +386,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        if (sub == SUB_PER_FLUSH - 1) {
-          fence_proxy_async();
-          named_bar_sync(1, EPI_THREADS);
-          if (ep_tid == 0) {
-            const int c0 = n0 + (sc / SUB_PER_FLUSH) * CH;
-            if (c0 < p.N) {
-              if (p.reduce_out) tma_reduce_add_2d(&tmD, buf, c0, m0);
-              else tma_store_2d(&tmD, buf, c0, m0);
-              if (dual) tma_store_2d(&tmD2, buf + OUT_BUF_BYTES, c0, m0);
-            }
-            tma_store_commit();
+        fence_proxy_async();
+        named_bar_sync(1, EPI_THREADS);
+        if (ep_tid == 0) {
+          const int c0 = n0 + c * CH;
+          if (c0 < p.N) {
+            if (p.reduce_out) tma_reduce_add_2d(&tmD, buf, c0, m0);
+            else tma_store_2d(&tmD, buf, c0, m0);
+            if (DUAL) tma_store_2d(&tmD2, buf + OUT_BUF_BYTES, c0, m0);
           }
-          ++flush;
+          tma_store_commit();
         }
+        ++flush;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (ep_tid == 0) tma_store_wait<0>();
   }
 
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp_idx == 1) {
+    __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CTAS == 2) {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                   ::"r"(tmem_base), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
+    } else {
+      tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
   }
 }
 
-template <int BN, bool OUT_F32>
+template <int BN, bool OUT_F32, int EF, int CTAS>
 int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTAS>;
   CUtensorMap tmA, tmB, tmD, tmD2;
   int rc;
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -324,29 +429,30 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   else        rc = make_tmap_2d(&tmA, bf, g.A, g.K, g.M, g.lda * 2, 64, BM);
   if (rc) return rc;
   if (g.b_mn) rc = make_tmap_2d(&tmB, bf, g.B, g.N, g.K, g.ldb * 2, 64, 64);
-  else        rc = make_tmap_2d(&tmB, bf, g.B, g.K, g.N, g.ldb * 2, 64, BN);
+  else        rc = make_tmap_2d(&tmB, bf, g.B, g.K, g.N, g.ldb * 2, 64, C::B_ROWS);
   if (rc) return rc;
   if (OUT_F32) rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, g.D, g.N, g.M, g.ldd * 4, 32, BM);
   else         rc = make_tmap_2d(&tmD, bf, g.D, g.N, g.M, g.ldd * 2, 64, BM);
   if (rc) return rc;
   tmD2 = tmD;
-  if (g.epi == EPI_BIAS_GELU) {
+  if (EF == EF_GELU) {
     rc = make_tmap_2d(&tmD2, bf, g.D2, g.N, g.M, g.ldd2 * 2, 64, BM);
     if (rc) return rc;
   }
 
   GemmDev p;
   p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
-  p.num_m_tiles = (int)((g.M + BM - 1) / BM);
+  p.num_m_tiles = (int)((g.M + BM * CTAS - 1) / (BM * CTAS));
   p.num_n_tiles = (int)((g.N + BN - 1) / BN);
   p.kblocks_total = (int)((g.K + BK - 1) / BK);
   int splits = g.splits;
   const int sms = num_sms();
-  if (splits <= 0) {            // auto: fill the machine when the output grid is small
+  const int slots = sms / CTAS;          // concurrently resident tiles
+  if (splits <= 0) {                     // auto: fill the machine when the output grid is small
     splits = 1;
     if (g.reduce_out) {
       int tiles = p.num_m_tiles * p.num_n_tiles;
-      if (tiles < sms) splits = sms / tiles;
+      if (tiles < slots) splits = slots / tiles;
     }
   }
   if (splits > p.kblocks_total) splits = p.kblocks_total;
@@ -358,14 +464,14 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
   splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
   p.total_tiles = p.num_m_tiles * p.num_n_tiles * splits;
-  p.a_mn = g.a_mn; p.b_mn = g.b_mn; p.epi = g.epi; p.reduce_out = g.reduce_out;
+  p.a_mn = g.a_mn; p.b_mn = g.b_mn; p.reduce_out = g.reduce_out;
   p.alpha = g.alpha;
   p.bias = g.bias;
   p.aux = reinterpret_cast<const bf16*>(g.aux);
   p.ldaux = g.ldaux;
   p.aux_row_mod = g.aux_row_mod;
 
-  auto kern = gemm_kernel<BN, OUT_F32>;
+  auto kern = gemm_kernel<BN, OUT_F32, EF, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -373,16 +479,48 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
     if (rc) return rc;
     attr_set = true;
   }
-  int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmD2, p);
-  return check_cuda(cudaGetLastError(), "gemm_kernel launch");
+  const int tiles_resident = p.total_tiles < slots ? p.total_tiles : slots;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(tiles_resident * CTAS));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmD2, p), "gemm_kernel launch");
+}
+
+template <int BN, int CTAS>
+int dispatch_epi(const GemmArgs& g, cudaStream_t s) {
+  const bool f32 = (g.out_dtype == DT_F32);
+  switch (g.epi) {
+    case EPI_NONE:
+    case EPI_BIAS:
+      return f32 ? launch_cfg<BN, true, EF_BIAS, CTAS>(g, s) : launch_cfg<BN, false, EF_BIAS, CTAS>(g, s);
+    case EPI_BIAS_RESID:
+      return f32 ? launch_cfg<BN, true, EF_RESID, CTAS>(g, s) : launch_cfg<BN, false, EF_RESID, CTAS>(g, s);
+    case EPI_BIAS_GELU:
+      return launch_cfg<BN, false, EF_GELU, CTAS>(g, s);
+    case EPI_DGELU:
+      if (f32) { set_error("bv_gemm: DGELU epilogue writes bf16"); return BV_ERR_INVALID; }
+      return launch_cfg<BN, false, EF_DGELU, CTAS>(g, s);
+  }
+  set_error("bv_gemm: bad epilogue %d", g.epi);
+  return BV_ERR_INVALID;
 }
 
 }  // namespace
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) { set_error("bv_gemm: empty problem"); return BV_ERR_INVALID; }
-  if (g.N % 8 != 0) { set_error("bv_gemm: N=%lld must be a multiple of 8", (long long)g.N); return BV_ERR_INVALID; }
+  // N need not be a multiple of 8 as long as the row strides are (TMA clips the store); bias / aux
+  // must then be readable up to round_up(N, 8) columns (see include/bv_b200.h).
+  if (g.ldd % 8 != 0 && g.out_dtype == DT_BF16) { set_error("bv_gemm: ldd must be a multiple of 8"); return BV_ERR_INVALID; }
   if (g.M > 0x7fffffffLL || g.N > 0x7fffffffLL || g.K > 0x7fffffffLL) {
     set_error("bv_gemm: dimension exceeds int32"); return BV_ERR_INVALID;
   }
@@ -399,16 +537,15 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.epi == EPI_BIAS_GELU && (g.out_dtype != DT_BF16 || g.D2 == nullptr || g.reduce_out)) {
     set_error("bv_gemm: BIAS_GELU needs bf16 output, D2 and no reduce"); return BV_ERR_INVALID;
   }
-  const bool f32 = (g.out_dtype == DT_F32);
-  if (!f32 && g.out_dtype != DT_BF16) { set_error("bv_gemm: bad out dtype"); return BV_ERR_INVALID; }
+  if (g.out_dtype != DT_F32 && g.out_dtype != DT_BF16) { set_error("bv_gemm: bad out dtype"); return BV_ERR_INVALID; }
   int bn = g.block_n;
-  if (bn == 0) {
-    const long long m_tiles = (g.M + BM - 1) / BM;
-    bn = (g.N % 256 == 0 || g.N >= 2048) ? 256 : 128;
-    if (bn == 256 && m_tiles * ((g.N + 255) / 256) < num_sms() / 2 && !g.reduce_out) bn = 128;
-  }
-  if (bn == 256) return f32 ? launch_cfg<256, true>(g, stream) : launch_cfg<256, false>(g, stream);
-  if (bn == 128) return f32 ? launch_cfg<128, true>(g, stream) : launch_cfg<128, false>(g, stream);
+  if (bn == 0) bn = (g.N > 128) ? 256 : 128;
+  // BV_GEMM_CTAS=1 selects the single-CTA (cta_group::1) build of the same kernel: a
+  // bring-up / A-B measurement switch, not a fallback (both are sm_100a tcgen05 paths).
+  static const int ctas = [] { const char* e = getenv("BV_GEMM_CTAS"); return (e && e[0] == '1') ? 1 : 2; }();
+  if (ctas == 1) return dispatch_epi<256, 1>(g, stream);
+  if (bn == 256) return dispatch_epi<256, 2>(g, stream);
+  if (bn == 128) return dispatch_epi<128, 2>(g, stream);
   set_error("bv_gemm: block_n must be 0, 128 or 256");
   return BV_ERR_INVALID;
 }

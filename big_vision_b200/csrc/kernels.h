@@ -50,7 +50,11 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 // ---- element-wise / reductions (elementwise.cu)
 int launch_patchify(const float* img, void* out, int64_t n, int H, int W, int C, int P,
                     cudaStream_t s);
-int launch_unpatchify_grad_unused();
+int launch_untranspose_add(const void* y, const void* res, void* out, int64_t n, int N, int d,
+                           cudaStream_t s);
+int launch_concat_cls(const void* x, const float* cls, void* out, int64_t n, int N0, int d,
+                      cudaStream_t s);
+int launch_drop_cls(const void* x, void* out, int64_t n, int N0, int d, cudaStream_t s);
 int launch_embed_fwd(const int32_t* ids, const float* table, const float* pos, void* out,
                      int out_dtype, int64_t n, int L, int d, int vocab, cudaStream_t s);
 int launch_embed_bwd(const int32_t* ids, const void* dy, int dy_dtype, float* dtable, float* dpos,

@@ -70,6 +70,9 @@ SIGNATURES = {
     "bv_gelu_fwd": [c_vp, c_vp, c_i32, c_i64, c_vp],
     "bv_axpby": [c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp],
     "bv_transpose_tokens": [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
+    "bv_untranspose_add": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
+    "bv_concat_cls": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
+    "bv_drop_cls": [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "bv_siglip_loss": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp,
                        c_vp, c_vp],
     "bv_sigmoid_xent": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],

@@ -383,7 +383,9 @@ class _Model:
                  aux=self._posemb16(P), aux_row_mod=N0, epilogue=L.EPI_BIAS_RESID)
     N = N0
     if self.pool_type == "tok":
-      raise NotImplementedError("pool_type='tok' (cls token) lands with the classification trainer")
+      # cls token is prepended AFTER the position embedding was added (models/vit.py:223-225)
+      x = ops.concat_cls(x, P.f(p + "cls").view(d), n, N0)
+      N = N0 + 1
     x, enc_saved = self.encoder.fwd(P, x, n, N)
     en = self.prefix + "Transformer/encoder_norm/"
     saved = {"patches": patches, "enc": enc_saved, "n": n, "N": N}
@@ -395,7 +397,7 @@ class _Model:
       encd, mean, rstd = ops.layernorm_fwd(x, P.f(en + "scale"), P.f(en + "bias"))
       saved["norm"] = (x, mean, rstd)
       out = ops.pool_fwd(encd, n, N, 0, out_dtype=torch.float32)
-    elif self.pool_type == "0":
+    elif self.pool_type in ("0", "tok"):
       # LayerNorm is per token, so LN(x)[:, 0] == LN(x[:, 0]): select first, normalise one row
       x0 = ops.pool_fwd(x, n, N, 1, tok=0)
       out, mean, rstd = ops.layernorm_fwd(x0, P.f(en + "scale"), P.f(en + "bias"), out_dtype=torch.float32)
@@ -454,9 +456,24 @@ class _Model:
       dx = ops.pool_bwd(dx0, n, N, 1, tok=0)
     # encoder: the column sum of the gradient reaching the embedding output is the patch-embed
     # bias gradient (models/vit.py:212-214)
-    dx = self.encoder.bwd(P, dx, saved["enc"], n, N, P.g(p + "embedding/bias"))
-    if self.posemb == "learn":
-      ops.colsum(dx.view(n, N * d), P.g(p + "pos_embedding").view(N * d))
+    if self.pool_type == "tok":
+      dx = self.encoder.bwd(P, dx, saved["enc"], n, N, None)
+      # batch-sum of the gradient at every token position: row 0 is d cls, the rest d pos_embedding;
+      # the patch-embed bias gradient is the sum of the latter over positions
+      N0 = N - 1
+      tmp = torch.zeros(N * d, dtype=torch.float32, device=dx.device)
+      ops.colsum(dx.view(n, N * d), tmp)
+      gcls = P.g(p + "cls").view(d)
+      ops.axpby(gcls, tmp[:d], 1.0, 1.0, out=gcls)
+      if self.posemb == "learn":
+        gpos = P.g(p + "pos_embedding").view(N0 * d)
+        ops.axpby(gpos, tmp[d:], 1.0, 1.0, out=gpos)
+      ops.colsum(tmp[d:].view(N0, d), P.g(p + "embedding/bias"))
+      dx = ops.drop_cls(dx, n, N0)
+    else:
+      dx = self.encoder.bwd(P, dx, saved["enc"], n, N, P.g(p + "embedding/bias"))
+      if self.posemb == "learn":
+        ops.colsum(dx.view(n, N * d), P.g(p + "pos_embedding").view(N * d))
     ops.gemm(saved["patches"], dx, a_mn=True, b_mn=True, out=P.g(p + "embedding/kernel_flat"), reduce_out=True)
 
   # ---- reference-style entry points --------------------------------------------------------

@@ -264,6 +264,26 @@ def transpose_tokens(x, n, N, d):
   return y
 
 
+def untranspose_add(y, res, n, N, d):
+  out = torch.empty((n * N, d), dtype=torch.bfloat16, device=y.device)
+  L.call("bv_untranspose_add", _p(y), _p(res), _p(out), n, N, d, _stream())
+  return out
+
+
+def concat_cls(x, cls, n, N0):
+  d = x.shape[-1]
+  out = torch.empty((n * (N0 + 1), d), dtype=torch.bfloat16, device=x.device)
+  L.call("bv_concat_cls", _p(x), _p(cls), _p(out), n, N0, d, _stream())
+  return out
+
+
+def drop_cls(x, n, N0):
+  d = x.shape[-1]
+  out = torch.empty((n * N0, d), dtype=torch.bfloat16, device=x.device)
+  L.call("bv_drop_cls", _p(x), _p(out), n, N0, d, _stream())
+  return out
+
+
 def siglip_loss(dots, row_offset, t_param, b_param, global_b, loss, dt, db):
   n, B = dots.shape
   G = torch.empty((n, B), dtype=torch.bfloat16, device=dots.device)

@@ -151,8 +151,18 @@ int bv_tanh_bwd(const void* dy, const void* y, void* dx, int dtype, int64_t n, v
 int bv_gelu_fwd(const void* x, void* y, int dtype, int64_t n, void* stream);
 int bv_axpby(const void* x, const void* y, void* out, int dtype, float a, float b, int64_t n,
              void* stream);
+/* cls token (models/vit.py:223-225): out[b,0,:] = cls, out[b,1+t,:] = x[b,t,:]  (bf16, cls fp32) */
+int bv_concat_cls(const void* x, const float* cls, void* out, int64_t n, int32_t N0, int32_t d,
+                  void* stream);
+/* out[b,t,:] = x[b,1+t,:] : the patch rows of a [n,N0+1,d] tensor (backward of the concat) */
+int bv_drop_cls(const void* x, void* out, int64_t n, int32_t N0, int32_t d, void* stream);
 /* bf16 [n,N,d] -> [n,d,round_up(N,8)] (zero pad): Mixer token mixing, mlp_mixer.py:49-51 */
 int bv_transpose_tokens(const void* x, void* y, int64_t n, int32_t N, int32_t d, void* stream);
+
+/* out[b,t,:] = (res ? res[b,t,:] : 0) + y[b,:,t], y stored [n,d,round_up(N,8)]: the transpose back
+ * fused with the residual add (mlp_mixer.py:51-52); res may be NULL */
+int bv_untranspose_add(const void* y, const void* res, void* out, int64_t n, int32_t N, int32_t d,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Losses

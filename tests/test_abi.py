@@ -42,7 +42,7 @@ def test_invalid_arguments_fail_loudly():
   rc = lib.bv_gemm(ctypes.byref(args), None)
   assert rc == -1
   assert b"empty" in lib.bv_last_error_string()
-  args = L.GemmArgs(M=8, N=12, K=8)   # N % 8 != 0
+  args = L.GemmArgs(M=8, N=8, K=8, ldd=12, out_dtype=L.BF16)   # bf16 row stride not 16B-aligned
   assert lib.bv_gemm(ctypes.byref(args), None) == -1
   with pytest.raises(L.BvError):
     L.call("bv_layernorm_fwd", None, 1, None, None, None, 1, None, None, 4, 12, 1e-6, None)

@@ -1,0 +1,97 @@
+"""GPU parity of the classification step (train.py update_fn: ViT with cls token / gap, MLP-Mixer;
+sigmoid_xent / softmax_xent) against the float64 oracle on tiny seeded configurations."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _randomize_zero_inits(tree, seed):
+  """Zero-initialised heads / cls would make most gradients vanish: give them small values
+  ('zero-init heads replaced by small normal for parity runs')."""
+  rng = np.random.default_rng(seed)
+  out = {}
+  for k, v in tree.items():
+    if not np.any(v):
+      out[k] = (rng.standard_normal(v.shape) * 0.05).astype(np.float32)
+    else:
+      out[k] = v
+  return out
+
+
+def _check(model, oracle_fwd, image_shape, loss_name, num_classes, seed=0):
+  from big_vision_b200 import train
+  P = model.init(seed, image_shape, device="cuda")
+  tree = _randomize_zero_inits(P.numpy_tree("f"), seed + 1)
+  P.load_tree(tree)
+  rng = np.random.default_rng(seed + 2)
+  image = rng.uniform(-1, 1, size=image_shape).astype(np.float32)
+  labels = np.eye(num_classes, dtype=np.float32)[rng.integers(0, num_classes, size=image_shape[0])]
+  loss, logits = train.loss_and_grads(model, P, torch.from_numpy(image).cuda(),
+                                      torch.from_numpy(labels).cuda(), loss_name)
+  # oracle
+  p64 = O.to_f64_tree(tree, requires_grad=True)
+  ref_logits_bf16 = oracle_fwd(O.to_f64_tree(tree), torch.from_numpy(image), "bfloat16")
+  ref_logits = oracle_fwd(p64, torch.from_numpy(image), "float32")
+  ref_loss = getattr(O, loss_name)(ref_logits, torch.from_numpy(labels).double())
+  ref_loss.backward()
+  scale = float(ref_logits.abs().max())
+  assert float((logits.double().cpu() - ref_logits_bf16).abs().max()) <= 2e-2 * scale
+  assert float((logits.double().cpu() - ref_logits.detach()).abs().max()) <= 6e-2 * scale
+  assert float(loss) == pytest.approx(float(ref_loss), rel=2e-2)
+  grads = P.numpy_tree("g")
+  gmax = max(float(v.grad.abs().max()) for v in p64.values() if v.grad is not None)
+  bad = {}
+  for k, g in grads.items():
+    ref = p64[k].grad.numpy() if p64[k].grad is not None else np.zeros_like(g)
+    err = float(np.abs(g.astype(np.float64) - ref).max())
+    tol = 6e-2 * float(np.abs(ref).max()) + 3e-3 * gmax
+    if err > tol:
+      bad[k] = (err, tol)
+  assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]
+
+
+@pytest.mark.parametrize("pool,posemb,rep,loss", [("tok", "learn", True, "sigmoid_xent"),
+                                                  ("gap", "sincos2d", True, "softmax_xent"),
+                                                  ("0", "learn", False, "sigmoid_xent")])
+def test_vit_classifier_step(pool, posemb, rep, loss):
+  from big_vision_b200.models import vit
+  kw = dict(width=64, depth=2, mlp_dim=128, num_heads=1, patch_size=(16, 16), pool_type=pool,
+            posemb=posemb, rep_size=rep)
+  model = vit.Model(16, **kw)
+  cfg = dict(depth=2, num_heads=1, pool_type=pool, posemb=posemb, rep_size=rep, num_classes=16)
+  _check(model, lambda p, img, mm: O.vit_forward(p, img, cfg, mm), (4, 64, 48, 3), loss, 16)
+
+
+def test_mlp_mixer_step():
+  from big_vision_b200.models import mlp_mixer
+  model = mlp_mixer.Model(16, patch_size=(16, 16), num_blocks=2, hidden_dim=64, tokens_mlp_dim=32,
+                          channels_mlp_dim=128)
+  cfg = dict(num_blocks=2, num_classes=16)
+  # 48 x 64 image -> 12 tokens: exercises the token padding (12 -> 16) of the token-mixing GEMMs
+  _check(model, lambda p, img, mm: O.mixer_forward(p, img, cfg, mm), (4, 48, 64, 3), "sigmoid_xent", 16)
+
+
+def test_classifier_update_fn_runs_and_learns():
+  from big_vision_b200 import optax as bv_optax, train
+  from big_vision_b200.models import vit
+  model = vit.Model(16, width=64, depth=2, mlp_dim=128, num_heads=1, patch_size=(16, 16),
+                    pool_type="tok", rep_size=True)
+  P = model.init(0, (8, 64, 64, 3), device="cuda")
+  P.load_tree(_randomize_zero_inits(P.numpy_tree("f"), 1))
+  config = dict(optax_name="scale_by_adam", optax=dict(mu_dtype="bfloat16"), lr=1e-3, wd=1e-4,
+                grad_clip_norm=1.0, loss="sigmoid_xent", schedule=dict(decay_type="cosine", warmup_steps=0))
+  tx, _ = bv_optax.make(config, P, sched_kw=dict(total_steps=100, batch_size=8, data_size=1000))
+  state = {"params": P, "opt": tx.init(P)}
+  fn = train.make_update_fn(model, tx, config)
+  rng = np.random.default_rng(0)
+  batch = {"image": torch.from_numpy(rng.uniform(-1, 1, (8, 64, 64, 3)).astype(np.float32)).cuda(),
+           "labels": torch.from_numpy(np.eye(16, dtype=np.float32)[rng.integers(0, 16, 8)]).cuda()}
+  losses = []
+  for _ in range(10):
+    state, m = fn(state, None, batch)
+    losses.append(float(m["training_loss"]))
+  assert losses[-1] < losses[0]
