@@ -37,7 +37,7 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
 // ============================================================================
 // forward
 // ============================================================================
-constexpr int FWD_THREADS = 320;   // warps 0-7 softmax/epilogue, 8 TMA, 9 MMA
+constexpr int FWD_THREADS = 352;   // warps 0-7 softmax/epilogue, 8 TMA, 9 S issue, 10 PV issue
 
 struct FwdDev {
   int tiles;          // B * H * QT
@@ -129,11 +129,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    // ---------------- MMA issuer ----------------
+    // ---------------- S = Q K^T issuer ----------------
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, p.NKP, 0, 0);   // Q K^T : both K-major
-      const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);      // P V   : V is MN-major
-      auto issue_s = [&](int i) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, p.NKP, 0, 0);   // both operands K-major
+      for (int i = 0; i < my_tiles; ++i) {
         const int st = i % p.nstage, bf = i % p.nbuf;
         mbar_wait(in_full(st), static_cast<uint32_t>(i / p.nstage) & 1u);
         mbar_wait(s_empty(bf), (static_cast<uint32_t>(i / p.nbuf) & 1u) ^ 1u);
@@ -147,15 +146,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                        umma_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(s_full(bf));
-      };
-      auto issue_pv = [&](int i) {
+      }
+    }
+  } else if (warp == 10) {
+    // ---------------- O = P V issuer ----------------
+    // A separate thread from the S issuer: waiting for the NEXT tile's TMA must never delay
+    // this tile's P V product.
+    if (lane == 0) {
+      const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);      // V is MN-major
+      const int ksteps = p.NKP / 16;
+      for (int i = 0; i < my_tiles; ++i) {
         const int st = i % p.nstage;
         mbar_wait(p_full, static_cast<uint32_t>(i) & 1u);
         mbar_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t v_s = base + st * L.stage_bytes + TILE_BYTES + L.kv_bytes;
         const uint32_t p_s = base + L.p_off;
-        const int ksteps = p.NKP / 16;
         for (int j = 0; j < ksteps; ++j) {
           const uint64_t ad = umma_smem_desc_sw128(p_s + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024);
           const uint64_t bd = umma_smem_desc_sw128(v_s + j * 2048, 8192, 1024);
@@ -163,18 +169,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         umma_commit(o_full);
         umma_commit(p_empty);
-        umma_commit(in_empty(st));
-      };
-      const bool ahead = (p.nstage == 2);
-      if (my_tiles > 0) issue_s(0);
-      for (int i = 0; i < my_tiles; ++i) {
-        if (ahead && i + 1 < my_tiles) issue_s(i + 1);
-        issue_pv(i);
-        if (!ahead && i + 1 < my_tiles) issue_s(i + 1);
+        umma_commit(in_empty(st));   // Q/K were consumed by S(i) long before (softmax(i) waited on it)
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ---------------- softmax + epilogue (8 warps) ----------------
+    // Software-pipelined: softmax(i+1) runs before epilogue(i), so the P V product of tile i
+    // and its TMEM->HBM write-out overlap the exponentials of tile i+1.
     const int quarter = warp & 3, hf = warp >> 2;
     const int row = quarter * 32 + lane;
     const int tid = threadIdx.x;            // 0..255
@@ -182,11 +183,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int half_cols = p.NKP >> 1;       // multiple of 8
     const int nunits = half_cols >> 3;      // <= 16
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    for (int i = 0; i < my_tiles; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      const int qt = tile % p.QT;
-      const int bh = tile / p.QT;
-      const int h = bh % p.H, b = bh / p.H;
+    const uint32_t p_s = base + L.p_off;
+    const uint32_t o_s = base + L.o_off;
+
+    // returns (1/sum, lse) of this thread's row for tile i
+    auto softmax = [&](int i, float& inv_out, float& lse_out) {
       const int bf = i % p.nbuf;
       mbar_wait(s_full(bf), static_cast<uint32_t>(i / p.nbuf) & 1u);
       tc_fence_after();
@@ -204,13 +205,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         if (u < nunits) {
+          const int c0 = hf * half_cols + u * 8;
+          if (c0 + 8 <= p.Nk) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = hf * half_cols + u * 8 + j;
-            float s = __uint_as_float(sv[u][j]) * p.scale_log2;
-            s = (col < p.Nk) ? s : -INFINITY;
-            sv[u][j] = __float_as_uint(s);
-            mx = fmaxf(mx, s);
+            for (int j = 0; j < 8; ++j) {
+              const float sc = __uint_as_float(sv[u][j]) * p.scale_log2;
+              sv[u][j] = __float_as_uint(sc);
+              mx = fmaxf(mx, sc);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float sc = __uint_as_float(sv[u][j]) * p.scale_log2;
+              sc = (c0 + j < p.Nk) ? sc : -INFINITY;
+              sv[u][j] = __float_as_uint(sc);
+              mx = fmaxf(mx, sc);
+            }
           }
         }
       }
@@ -218,8 +228,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(2, 256);
       mx = fmaxf(mx, xch[(hf ^ 1) * 128 + row]);
       float sum = 0.f;
-      mbar_wait(p_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
-      const uint32_t p_s = base + L.p_off;
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         if (u < nunits) {
@@ -229,12 +237,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             e[j] = exp2f(__uint_as_float(sv[u][j]) - mx);
             sum += e[j];
           }
+          // packed in place: sv[u][0..3] now hold the 8 bf16 probabilities of this unit
+          sv[u][0] = pack_bf16(e[0], e[1]); sv[u][1] = pack_bf16(e[2], e[3]);
+          sv[u][2] = pack_bf16(e[4], e[5]); sv[u][3] = pack_bf16(e[6], e[7]);
+        }
+      }
+      // the P buffer is free once the previous tile's P V product has retired
+      mbar_wait(p_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (u < nunits) {
           const int c0 = hf * half_cols + u * 8;
           const uint32_t addr = p_s + (c0 >> 6) * TILE_BYTES + row * 128 +
                                 ((static_cast<uint32_t>((c0 & 63) >> 3) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_bf16(e[0], e[1])), "r"(pack_bf16(e[2], e[3])),
-                       "r"(pack_bf16(e[4], e[5])), "r"(pack_bf16(e[6], e[7])) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sv[u][0]),
+                       "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
         }
       }
       xch[256 + hf * 128 + row] = sum;
@@ -243,8 +260,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) mbar_arrive(p_full);
       named_bar_sync(2, 256);
       sum += xch[256 + (hf ^ 1) * 128 + row];
+      inv_out = 1.0f / sum;
+      lse_out = (mx + log2f(sum)) * LN2;
+    };
 
-      // ---- epilogue: O / sum -> bf16 -> smem -> TMA store
+    auto epilogue = [&](int i, float inv, float lse_val) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int qt = tile % p.QT;
+      const int bh = tile / p.QT;
+      const int h = bh % p.H, b = bh / p.H;
       mbar_wait(o_full, static_cast<uint32_t>(i) & 1u);
       tc_fence_after();
       uint32_t ov[32];
@@ -253,10 +277,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-      const float inv = 1.0f / sum;
       if (tid == 0) tma_store_wait_read<0>();
       named_bar_sync(2, 256);
-      const uint32_t o_s = base + L.o_off;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
@@ -270,16 +292,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const int qrow = qt * TQ + row;
       if (hf == 0 && qrow < p.Nq && p.lse != nullptr)
-        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Nq + qrow] = (mx + log2f(sum)) * LN2;
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Nq + qrow] = lse_val;
       fence_proxy_async();
       named_bar_sync(2, 256);
       if (tid == 0) {
         tma_store_3d(&tmO, o_s, h * DH, qt * TQ, b);
         tma_store_commit();
       }
+    };
+
+    float inv_cur = 0.f, lse_cur = 0.f;
+    if (my_tiles > 0) softmax(0, inv_cur, lse_cur);
+    for (int i = 0; i < my_tiles; ++i) {
+      float inv_nxt = 0.f, lse_nxt = 0.f;
+      if (i + 1 < my_tiles) softmax(i + 1, inv_nxt, lse_nxt);
+      epilogue(i, inv_cur, lse_cur);
+      inv_cur = inv_nxt;
+      lse_cur = lse_nxt;
     }
     if (tid == 0) tma_store_wait<0>();
   }
+  __syncwarp();
   tc_fence_before();
   __syncthreads();
   if (warp == 9) {
@@ -355,7 +388,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int my_items = (p.BH - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                        static_cast<int>(gridDim.x);
-  const int pairs = p.KT * p.QT;
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -382,51 +414,65 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t id_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
       const uint32_t id_mm = umma_idesc_bf16(128, DH, 1, 1);    // dV, dK : A^T (MN) x B (MN)
       const uint32_t id_km = umma_idesc_bf16(128, DH, 0, 1);    // dQ     : A (K)  x B (MN)
-      uint32_t pair_cnt = 0, kt_cnt = 0;
+      uint32_t sdp_cnt = 0, grad_cnt = 0, kt_cnt = 0;
+      const int pairs = p.KT * p.QT;
+      // S = Q K^T and dP = dO V^T of pair j (kt outer, qt inner) into TMEM
+      auto issue_sdp = [&](int j) {
+        const int kt = j / p.QT, qt = j % p.QT;
+        mbar_wait(sdp_empty, (sdp_cnt & 1u) ^ 1u);
+        ++sdp_cnt;
+        tc_fence_after();
+        const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
+        const uint32_t va = v_s + kt * TILE_BYTES, da = do_s + qt * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + S_COL, umma_smem_desc_sw128(qa + k * 32, 16, 1024),
+                       umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + DP_COL, umma_smem_desc_sw128(da + k * 32, 16, 1024),
+                       umma_smem_desc_sw128(va + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
+        umma_commit(sdp_full);
+      };
+      // dV, dK, dQ contributions of pair j from the P / dS tiles the compute warps wrote
+      auto issue_grads = [&](int j, uint32_t ph) {
+        const int kt = j / p.QT, qt = j % p.QT;
+        const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
+        const uint32_t da = do_s + qt * TILE_BYTES;
+        mbar_wait(pds_full, grad_cnt & 1u);
+        ++grad_cnt;
+        if (qt == 0) mbar_wait(dkv_empty, (kt_cnt & 1u) ^ 1u);
+        if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {   // contraction over 128 query rows, 16 per step
+          const uint64_t a_p = umma_smem_desc_sw128(p_s + jj * 2048, TILE_BYTES, 1024);
+          const uint64_t a_ds = umma_smem_desc_sw128(ds_s + jj * 2048, TILE_BYTES, 1024);
+          const uint64_t b_do = umma_smem_desc_sw128(da + jj * 2048, 8192, 1024);
+          const uint64_t b_q = umma_smem_desc_sw128(qa + jj * 2048, 8192, 1024);
+          const uint32_t accv = (qt > 0 || jj > 0) ? 1u : 0u;
+          umma_bf16_ss(tmem_base + DV_COL, a_p, b_do, id_mm, accv);
+          umma_bf16_ss(tmem_base + DK_COL, a_ds, b_q, id_mm, accv);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {   // contraction over 128 keys
+          const uint64_t a_ds = umma_smem_desc_sw128(ds_s + (jj >> 2) * TILE_BYTES + (jj & 3) * 32, 16, 1024);
+          const uint64_t b_k = umma_smem_desc_sw128(ka + jj * 2048, 8192, 1024);
+          umma_bf16_ss(tmem_base + DQ_COL + qt * DH, a_ds, b_k, id_km, (kt > 0 || jj > 0) ? 1u : 0u);
+        }
+        umma_commit(pds_empty);
+        if (qt == p.QT - 1) { umma_commit(dkv_full); ++kt_cnt; }
+      };
       for (int it = 0; it < my_items; ++it) {
         const uint32_t ph = static_cast<uint32_t>(it) & 1u;
         mbar_wait(in_full, ph);
         mbar_wait(stat_ready, ph);   // the compute warps are done with O in the P buffer
-        for (int kt = 0; kt < p.KT; ++kt) {
-          for (int qt = 0; qt < p.QT; ++qt, ++pair_cnt) {
-            const uint32_t pp = pair_cnt & 1u;
-            mbar_wait(sdp_empty, pp ^ 1u);
-            tc_fence_after();
-            const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
-            const uint32_t va = v_s + kt * TILE_BYTES, da = do_s + qt * TILE_BYTES;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_base + S_COL, umma_smem_desc_sw128(qa + k * 32, 16, 1024),
-                           umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss(tmem_base + DP_COL, umma_smem_desc_sw128(da + k * 32, 16, 1024),
-                           umma_smem_desc_sw128(va + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
-            umma_commit(sdp_full);
-
-            mbar_wait(pds_full, pp);
-            if (qt == 0) mbar_wait(dkv_empty, (kt_cnt & 1u) ^ 1u);
-            if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {   // contraction over 128 query rows, 16 per step
-              const uint64_t a_p = umma_smem_desc_sw128(p_s + j * 2048, TILE_BYTES, 1024);
-              const uint64_t a_ds = umma_smem_desc_sw128(ds_s + j * 2048, TILE_BYTES, 1024);
-              const uint64_t b_do = umma_smem_desc_sw128(da + j * 2048, 8192, 1024);
-              const uint64_t b_q = umma_smem_desc_sw128(qa + j * 2048, 8192, 1024);
-              const uint32_t accv = (qt > 0 || j > 0) ? 1u : 0u;
-              umma_bf16_ss(tmem_base + DV_COL, a_p, b_do, id_mm, accv);
-              umma_bf16_ss(tmem_base + DK_COL, a_ds, b_q, id_mm, accv);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {   // contraction over 128 keys
-              const uint64_t a_ds = umma_smem_desc_sw128(ds_s + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024);
-              const uint64_t b_k = umma_smem_desc_sw128(ka + j * 2048, 8192, 1024);
-              umma_bf16_ss(tmem_base + DQ_COL + qt * DH, a_ds, b_k, id_km, (kt > 0 || j > 0) ? 1u : 0u);
-            }
-            umma_commit(pds_empty);
-            if (qt == p.QT - 1) { umma_commit(dkv_full); ++kt_cnt; }
-          }
+        // software pipeline: S/dP of pair j+1 are issued BEFORE the gradient products of pair j,
+        // so the compute warps can start on pair j+1 while the tensor core finishes pair j
+        issue_sdp(0);
+        for (int j = 0; j < pairs; ++j) {
+          if (j + 1 < pairs) issue_sdp(j + 1);
+          issue_grads(j, ph);
         }
         umma_commit(dq_full);
         umma_commit(in_empty);

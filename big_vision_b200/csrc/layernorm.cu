@@ -231,7 +231,7 @@ int launch_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, con
   if (rows == 0) return BV_OK;
   const int nch = (d / 8 + 31) / 32;
   int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
-  const int64_t cap = static_cast<int64_t>(num_sms()) * 4;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 2;   // 2 resident blocks/SM (register-bound)
   if (blocks > cap) blocks = cap;
   const size_t smem = 3 * static_cast<size_t>(d) * sizeof(float);
 #define LN_BWD_CASE(N)                                                                         \

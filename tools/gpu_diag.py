@@ -361,7 +361,7 @@ CHECKS = {
 
 
 def main():
-  if len(sys.argv) > 1 and sys.argv[1] in CHECKS:
+  if len(sys.argv) == 2 and sys.argv[1] in CHECKS:
     ok = CHECKS[sys.argv[1]]()
     import torch
     torch.cuda.synchronize()
