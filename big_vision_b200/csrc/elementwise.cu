@@ -133,7 +133,26 @@ colsum_kernel(const void* __restrict__ x, int dt, float* __restrict__ out, int64
   int64_t r1 = r0 + CS_ROWS_PER_BLOCK;
   if (r1 > rows) r1 = rows;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (c0 < cols) {
+  if (c0 < cols && dt == DT_BF16) {
+    // 4 independent 16-byte loads in flight per thread
+    const bf16* xb = reinterpret_cast<const bf16*>(x);
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(xb + (r + 8 * u) * ld + c0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(q[u].x); acc[1] += bf16_hi(q[u].x); acc[2] += bf16_lo(q[u].y); acc[3] += bf16_hi(q[u].y);
+        acc[4] += bf16_lo(q[u].z); acc[5] += bf16_hi(q[u].z); acc[6] += bf16_lo(q[u].w); acc[7] += bf16_hi(q[u].w);
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 q = *reinterpret_cast<const uint4*>(xb + r * ld + c0);
+      acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+      acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+    }
+  } else if (c0 < cols) {
     for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
       if (dt == DT_BF16) {
         const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x) + r * ld + c0);

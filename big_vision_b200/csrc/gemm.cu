@@ -44,14 +44,19 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 // epilogue families (template parameter)
 enum : int { EF_BIAS = 0, EF_GELU = 1, EF_RESID = 2, EF_DGELU = 3 };
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, bool DUAL_OUT>
 struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;                 // rows of B this CTA loads
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
+  // staging buffers for the TMA stores: 2 (double-buffered), or 2 x 2 when the epilogue
+  // writes two tensors (gelu output + pre-activation)
+  static constexpr int OUT_BUFS = DUAL_OUT ? 4 : 2;
+  static constexpr int SMEM_LIMIT = 232448 - 1280;         // 227 KB minus barriers / align slack
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - OUT_BUFS * OUT_BUF_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256 (power of two)
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + 2 * OUT_BUF_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + OUT_BUFS * OUT_BUF_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
 };
 
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
             const GemmDev p) {
-  using C = Cfg<BN, CTAS>;
+  using C = Cfg<BN, CTAS, EF == EF_GELU>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -284,35 +289,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
       int m0, n0, kb0, kb1;
       decode_tile(tile, m0, n0, kb0, kb1);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int grow = m0 + row;
       const bool row_ok = grow < p.M;
-      const bf16* aux_row = nullptr;
-      if ((EF == EF_RESID || EF == EF_DGELU) && row_ok) {
-        long long ar = p.aux_row_mod > 0 ? (grow % p.aux_row_mod) : grow;
-        aux_row = p.aux + ar * p.ldaux;
+      // The residual / pre-activation operand of this thread's row for the WHOLE tile is fetched
+      // before waiting for the accumulator, so its HBM/L2 latency hides behind the mainloop.
+      constexpr bool HAS_AUX = (EF == EF_RESID || EF == EF_DGELU);
+      constexpr int NAUX = HAS_AUX ? NCHUNK * (WC / 8) : 1;
+      uint4 aq_all[NAUX];
+      if (HAS_AUX) {
+        const bf16* aux_row = nullptr;
+        if (row_ok) {
+          long long ar = p.aux_row_mod > 0 ? (grow % p.aux_row_mod) : grow;
+          aux_row = p.aux + ar * p.ldaux;
+        }
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+#pragma unroll
+          for (int g = 0; g < WC / 8; ++g) {
+            const int nc = n0 + c * CH + half * WC + g * 8;
+            aq_all[c * (WC / 8) + g] = make_uint4(0u, 0u, 0u, 0u);
+            if (aux_row != nullptr && nc < p.N)
+              aq_all[c * (WC / 8) + g] = *reinterpret_cast<const uint4*>(aux_row + nc);
+          }
+        }
       }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
-        const uint32_t buf = DUAL ? out_buf : out_buf + (flush & 1u) * OUT_BUF_BYTES;
+        // double-buffered staging: one buffer (or one act/pre pair) per in-flight TMA store
+        const uint32_t buf = out_buf + (flush & 1u) * (DUAL ? 2 : 1) * OUT_BUF_BYTES;
         const int col_t = c * CH + half * WC;       // first column (within the tile) of this warp
         const int ncol0 = n0 + col_t;
         uint32_t r[WC];
         if constexpr (OUT_F32) tmem_ld_32x32b_x16(t_row + col_t, r);
         else tmem_ld_32x32b_x32(t_row + col_t, r);
-        // issue the aux loads while the TMEM load is in flight
-        uint4 aq[WC / 8];
-        if (EF == EF_RESID || EF == EF_DGELU) {
-#pragma unroll
-          for (int g = 0; g < WC / 8; ++g) {
-            aq[g] = make_uint4(0u, 0u, 0u, 0u);
-            if (aux_row != nullptr && ncol0 + g * 8 < p.N)
-              aq[g] = *reinterpret_cast<const uint4*>(aux_row + ncol0 + g * 8);
-          }
-        }
         tmem_ld_wait();
         if (c == NCHUNK - 1) {
           // accumulator fully drained into registers -> hand TMEM back to the MMA warp
@@ -324,9 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         // make sure the TMA store that last used this staging buffer has read it
-        if (ep_tid == 0) {
-          if (DUAL) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-        }
+        if (ep_tid == 0) tma_store_wait_read<1>();
         named_bar_sync(1, EPI_THREADS);
 #pragma unroll
         for (int g = 0; g < WC / 8; ++g) {      // 8 columns per group
@@ -353,7 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[i] = gelu_tanh_fast(v2[i]);
             }
           } else if (EF == EF_RESID || EF == EF_DGELU) {
-            const uint4 q = aq[g];
+            const uint4 q = aq_all[c * (WC / 8) + g];
             const float a[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                 bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
             if (EF == EF_RESID) {
@@ -421,7 +432,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int BN, bool OUT_F32, int EF, int CTAS>
 int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
-  using C = Cfg<BN, CTAS>;
+  using C = Cfg<BN, CTAS, EF == EF_GELU>;
   CUtensorMap tmA, tmB, tmD, tmD2;
   int rc;
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;

@@ -189,6 +189,192 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_dt, const void* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------------------
+// bf16 fast path of the backward: same math, but every warp streams its rows through a private
+// shared-memory ring filled by cp.async (16 B per lane per request), DEPTH rows ahead of the
+// arithmetic.  Memory-level parallelism then no longer depends on registers: 8 warps x
+// (DEPTH-1) rows x 4.5 KB are in flight per SM, enough to cover HBM latency.
+// ---------------------------------------------------------------------------
+constexpr int LNP_DEPTH = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
+  uint4 q;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+  v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+  v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+}
+
+template <int NCH, bool HAS_RES>
+__global__ void __launch_bounds__(LN_THREADS, 1)
+ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                   const float* __restrict__ scale, const float* __restrict__ mean_in,
+                   const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
+                   bf16* __restrict__ dx, float* __restrict__ dscale, float* __restrict__ dbias,
+                   float* __restrict__ dx_colsum, int64_t rows, int d) {
+  extern __shared__ __align__(16) uint8_t smem_ln[];
+  constexpr int NARR = HAS_RES ? 3 : 2;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nchunks = d >> 3;
+  const bool want_cs = dx_colsum != nullptr;
+  float* red = reinterpret_cast<float*>(smem_ln);                       // [3][d]
+  const int row_bytes = d * 2;
+  const uint32_t ring = smem_u32(smem_ln) + 3 * d * 4 + warp * (LNP_DEPTH * NARR * row_bytes);
+  for (int i = threadIdx.x; i < 3 * d; i += LN_THREADS) red[i] = 0.f;
+  __syncthreads();
+
+  float acc_g[NCH][8], acc_b[NCH][8], acc_c[NCH][8];
+  float g[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc_g[i][j] = 0.f; acc_b[i][j] = 0.f; acc_c[i][j] = 0.f; g[i][j] = 0.f; }
+    if (c < nchunks) load8f(scale + c * 8, g[i]);
+  }
+  const float inv_d = 1.0f / static_cast<float>(d);
+  const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * LN_WARPS;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp;
+
+  auto issue = [&](int64_t row, int slot) {
+    if (row < rows) {
+      const uint32_t sbase = ring + slot * (NARR * row_bytes);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nchunks) {
+          const int64_t off = row * d + c * 8;
+          cp_async16(sbase + c * 16, x + off);
+          cp_async16(sbase + row_bytes + c * 16, dy + off);
+          if (HAS_RES) cp_async16(sbase + 2 * row_bytes + c * 16, dres + off);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int k = 0; k < LNP_DEPTH - 1; ++k) issue(row0 + k * warp_stride, k);
+
+  int slot = 0;
+  for (int64_t row = row0; row < rows; row += warp_stride) {
+    issue(row + (LNP_DEPTH - 1) * warp_stride, (slot + LNP_DEPTH - 1) % LNP_DEPTH);
+    cp_async_wait<LNP_DEPTH - 1>();
+    __syncwarp();
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const uint32_t sbase = ring + slot * (NARR * row_bytes);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float xv[8], dv[8];
+        lds8(sbase + c * 16, xv);
+        lds8(sbase + row_bytes + c * 16, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float gy = dv[j] * g[i][j];
+          c1 += gy;
+          c2 += gy * xh;
+          acc_g[i][j] += dv[j] * xh;
+          acc_b[i][j] += dv[j];
+        }
+      }
+    }
+    c1 = warp_sum(c1) * inv_d;
+    c2 = warp_sum(c2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float xv[8], dv[8], o[8];
+        lds8(sbase + c * 16, xv);
+        lds8(sbase + row_bytes + c * 16, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          o[j] = rstd * (dv[j] * g[i][j] - c1 - xh * c2);
+        }
+        if (HAS_RES) {
+          float r[8];
+          lds8(sbase + 2 * row_bytes + c * 16, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = round_bf16(o[j]);
+        store8(dx, DT_BF16, row * d + c * 8, o);
+        if (want_cs) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc_c[i][j] += o[j];
+        }
+      }
+    }
+    __syncwarp();   // all lanes done with this slot before it is refilled next iteration
+    slot = (slot + 1) % LNP_DEPTH;
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[c * 8 + j], acc_g[i][j]);
+        atomicAdd(&red[d + c * 8 + j], acc_b[i][j]);
+        if (want_cs) atomicAdd(&red[2 * d + c * 8 + j], acc_c[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += LN_THREADS) {
+    if (dscale) atomicAdd(dscale + i, red[i]);
+    if (dbias) atomicAdd(dbias + i, red[d + i]);
+    if (want_cs) atomicAdd(dx_colsum + i, red[2 * d + i]);
+  }
+}
+
+template <int NCH>
+int launch_ln_bwd_pipe(const void* dy, const void* x, const float* scale, const float* mean,
+                       const float* rstd, const void* dres, void* dx, float* dscale, float* dbias,
+                       float* dx_colsum, int64_t rows, int d, cudaStream_t s) {
+  const int narr = dres ? 3 : 2;
+  const size_t smem = 3 * static_cast<size_t>(d) * 4 +
+                      static_cast<size_t>(LN_WARPS) * LNP_DEPTH * narr * d * 2;
+  int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int64_t cap = num_sms();
+  if (blocks > cap) blocks = cap;
+  cudaError_t e;
+  if (dres) {
+    auto k = ln_bwd_pipe_kernel<NCH, true>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_bwd_pipe)");
+    k<<<(unsigned)blocks, LN_THREADS, smem, s>>>(
+        reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), scale, mean, rstd,
+        reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dscale, dbias, dx_colsum, rows, d);
+  } else {
+    auto k = ln_bwd_pipe_kernel<NCH, false>;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_bwd_pipe)");
+    k<<<(unsigned)blocks, LN_THREADS, smem, s>>>(
+        reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), scale, mean, rstd,
+        nullptr, reinterpret_cast<bf16*>(dx), dscale, dbias, dx_colsum, rows, d);
+  }
+  return check_cuda(cudaGetLastError(), "ln_bwd_pipe_kernel launch");
+}
+
 int check_ln(int64_t rows, int d, const char* who) {
   if (rows < 0 || d <= 0 || d % 8 != 0 || d > 2048) {
     set_error("%s: need rows >= 0 and d %% 8 == 0, d <= 2048 (got rows=%lld d=%d)", who,
@@ -230,6 +416,21 @@ int launch_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, con
   if (rc) return rc;
   if (rows == 0) return BV_OK;
   const int nch = (d / 8 + 31) / 32;
+  {
+    // streaming bf16 fast path (cp.async ring); the generic kernel below covers fp32 operands,
+    // small problems and widths whose ring does not fit in shared memory
+    const size_t ring = 3 * static_cast<size_t>(d) * 4 +
+                        static_cast<size_t>(LN_WARPS) * LNP_DEPTH * (dres ? 3 : 2) * d * 2;
+    if (dy_dt == DT_BF16 && x_dt == DT_BF16 && dx_dt == DT_BF16 && rows >= 4096 && nch <= 4 &&
+        ring <= 220 * 1024) {
+      switch (nch) {
+        case 1: return launch_ln_bwd_pipe<1>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
+        case 2: return launch_ln_bwd_pipe<2>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
+        case 3: return launch_ln_bwd_pipe<3>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
+        default: return launch_ln_bwd_pipe<4>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
+      }
+    }
+  }
   int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 2;   // 2 resident blocks/SM (register-bound)
   if (blocks > cap) blocks = cap;
