@@ -16,6 +16,8 @@
 #include "host_utils.h"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace bv {
 namespace {
 
@@ -45,7 +47,15 @@ struct FwdDev {
   int nstage, nbuf;
   float scale_log2;   // scale * log2(e)
   float* lse;         // [B, H, Nq]
+  long long* dbg;     // optional timeline of CTA 0 (bring-up aid, BV_ATTN_DBG=1), else null
 };
+
+// dbg[(tile_i * 16 + event)] = clock64() for the first 32 tiles of CTA 0
+#define ATTN_DBG(ev, i)                                                       \
+  do {                                                                        \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (i) < 32)                      \
+      p.dbg[(i) * 16 + (ev)] = clock64();                                     \
+  } while (0)
 
 struct FwdSmem {
   // byte offsets from the 1024-aligned base
@@ -126,6 +136,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_3d(q_s, &tmQ, in_full(st), h * DH, qt * TQ, b);
         tma_load_3d(k_s, &tmK, in_full(st), h * DH, 0, b);
         tma_load_3d(v_s, &tmV, in_full(st), h * DH, 0, b);
+        ATTN_DBG(0, i);
       }
     }
   } else if (warp == 9) {
@@ -137,6 +148,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(in_full(st), static_cast<uint32_t>(i / p.nstage) & 1u);
         mbar_wait(s_empty(bf), (static_cast<uint32_t>(i / p.nbuf) & 1u) ^ 1u);
         tc_fence_after();
+        ATTN_DBG(1, i);
         const uint32_t q_s = base + st * L.stage_bytes;
         const uint32_t k_s = q_s + TILE_BYTES;
         const uint32_t d = tmem_base + bf * p.NKP;
@@ -146,6 +158,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                        umma_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         }
         umma_commit(s_full(bf));
+        ATTN_DBG(2, i);
       }
     }
   } else if (warp == 10) {
@@ -160,6 +173,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(p_full, static_cast<uint32_t>(i) & 1u);
         mbar_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
         tc_fence_after();
+        ATTN_DBG(7, i);
         const uint32_t v_s = base + st * L.stage_bytes + TILE_BYTES + L.kv_bytes;
         const uint32_t p_s = base + L.p_off;
         for (int j = 0; j < ksteps; ++j) {
@@ -169,6 +183,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         umma_commit(o_full);
         umma_commit(p_empty);
+        ATTN_DBG(8, i);
         umma_commit(in_empty(st));   // Q/K were consumed by S(i) long before (softmax(i) waited on it)
       }
     }
@@ -191,6 +206,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int bf = i % p.nbuf;
       mbar_wait(s_full(bf), static_cast<uint32_t>(i / p.nbuf) & 1u);
       tc_fence_after();
+      if (tid == 0) ATTN_DBG(3, i);
       uint32_t sv[16][8];
       const uint32_t s_addr = tmem_base + lane_addr + bf * p.NKP + hf * half_cols;
 #pragma unroll
@@ -227,6 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       xch[hf * 128 + row] = mx;
       named_bar_sync(2, 256);
       mx = fmaxf(mx, xch[(hf ^ 1) * 128 + row]);
+      if (tid == 0) ATTN_DBG(4, i);
       float sum = 0.f;
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
@@ -244,6 +261,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // the P buffer is free once the previous tile's P V product has retired
       mbar_wait(p_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+      if (tid == 0) ATTN_DBG(5, i);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         if (u < nunits) {
@@ -258,6 +276,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (tid == 0) ATTN_DBG(6, i);
       named_bar_sync(2, 256);
       sum += xch[256 + (hf ^ 1) * 128 + row];
       inv_out = 1.0f / sum;
@@ -271,6 +290,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int h = bh % p.H, b = bh / p.H;
       mbar_wait(o_full, static_cast<uint32_t>(i) & 1u);
       tc_fence_after();
+      if (tid == 0) ATTN_DBG(9, i);
       uint32_t ov[32];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + hf * 32, ov);
       tmem_ld_wait();
@@ -279,6 +299,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) mbar_arrive(o_empty);
       if (tid == 0) tma_store_wait_read<0>();
       named_bar_sync(2, 256);
+      if (tid == 0) ATTN_DBG(10, i);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
@@ -298,6 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (tid == 0) {
         tma_store_3d(&tmO, o_s, h * DH, qt * TQ, b);
         tma_store_commit();
+        ATTN_DBG(11, i);
       }
     };
 
@@ -668,10 +690,30 @@ int check_attn(const AttnArgs& a, const char* who) {
 
 }  // namespace
 
+static long long* g_attn_dbg = nullptr;
+
+long long* attn_debug_buffer() {
+  static const bool on = [] { const char* e = getenv("BV_ATTN_DBG"); return e && e[0] == '1'; }();
+  if (!on) return nullptr;
+  if (g_attn_dbg == nullptr) {
+    if (cudaMalloc(&g_attn_dbg, 32 * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
+  }
+  cudaMemset(g_attn_dbg, 0, 32 * 16 * sizeof(long long));
+  return g_attn_dbg;
+}
+int attn_debug_read(long long* host, int n) {
+  if (g_attn_dbg == nullptr) return 0;
+  if (n > 32 * 16) n = 32 * 16;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host, g_attn_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
+}
+
 int launch_attention_fwd(const AttnArgs& a, cudaStream_t s) {
   int rc = check_attn(a, "bv_attention_fwd");
   if (rc) return rc;
   FwdDev p;
+  p.dbg = attn_debug_buffer();
   p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
   p.QT = (a.Nq + TQ - 1) / TQ;
   p.NKP = (a.Nk + 15) / 16 * 16;

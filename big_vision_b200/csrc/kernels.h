@@ -46,6 +46,7 @@ struct AttnBwdArgs {
   float* delta;                                  // workspace [B, H, Nq]
 };
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
+int attn_debug_read(long long* host, int n);   // BV_ATTN_DBG=1 timeline of the last fwd launch
 
 // ---- element-wise / reductions (elementwise.cu)
 int launch_patchify(const float* img, void* out, int64_t n, int H, int W, int C, int P,
