@@ -39,7 +39,7 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
 // ============================================================================
 // forward
 // ============================================================================
-constexpr int FWD_THREADS = 352;   // warps 0-7 softmax/epilogue, 8 TMA, 9 S issue, 10 PV issue
+constexpr int FWD_THREADS = 512;   // WG0,1 softmax; WG2: TMA / S issue / PV issue; WG3: O epilogue
 
 struct FwdDev {
   int tiles;          // B * H * QT
@@ -70,9 +70,35 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int NKP, int nstage) {
   const int nblk = (NKP + 63) / 64;
   L.o_off = L.p_off + nblk * TILE_BYTES;
   L.x_off = L.o_off + TILE_BYTES;
-  L.bar_off = L.x_off + 4 * 128 * 4;
-  L.total = L.bar_off + 128 + 1024;
+  L.bar_off = L.x_off + 6 * 128 * 4;
+  L.total = L.bar_off + 160 + 1024;
   return L;
+}
+
+template <int R> __device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
+}
+template <int R> __device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
+}
+__device__ __forceinline__ float ex2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5,
+// degree-4 polynomial for 2^f (rel. error < 5e-5, far inside the bf16 rounding of P), exponent
+// patched in with integer arithmetic.  B200's MUFU.EX2 sustains ~8 lanes/clk/SM, which makes the
+// exponentials the bound of the softmax; splitting them between MUFU and this path doubles the rate.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;     // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float pl = fmaf(f, 0.0096181291f, 0.0555041087f);
+  pl = fmaf(pl, f, 0.2402265070f);
+  pl = fmaf(pl, f, 0.6931471806f);
+  pl = fmaf(pl, f, 1.0f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
 }
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
@@ -91,9 +117,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   auto s_full = [&](int b) { return bar + 8u * (4 + b); };
   auto s_empty = [&](int b) { return bar + 8u * (6 + b); };
   const uint32_t p_full = bar + 64, p_empty = bar + 72, o_full = bar + 80, o_empty = bar + 88;
-  const uint32_t tmem_slot = bar + 96;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L.bar_off + 96);
-  float* xch = reinterpret_cast<float*>(base_ptr + L.x_off);   // [max0|max1|sum0|sum1][128]
+  auto inv_full = [&](int b) { return bar + 96u + 8u * b; };
+  auto inv_empty = [&](int b) { return bar + 112u + 8u * b; };
+  const uint32_t tmem_slot = bar + 128;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + L.bar_off + 128);
+  float* xch = reinterpret_cast<float*>(base_ptr + L.x_off);   // [max0|max1|sum0|sum1|inv0|inv1][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,9 +131,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(in_full(s), 1); mbar_init(in_empty(s), 1);
       mbar_init(s_full(s), 1);  mbar_init(s_empty(s), 8);
+      mbar_init(inv_full(s), 8); mbar_init(inv_empty(s), 4);
     }
     mbar_init(p_full, 8); mbar_init(p_empty, 1);
-    mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    mbar_init(o_full, 1); mbar_init(o_empty, 4);
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -118,79 +147,131 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int my_tiles = (p.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                        static_cast<int>(gridDim.x);
 
-  if (warp == 8) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      for (int i = 0; i < my_tiles; ++i) {
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int qt = tile % p.QT;
-        const int bh = tile / p.QT;
-        const int h = bh % p.H, b = bh / p.H;
-        const int st = i % p.nstage;
-        const uint32_t ph = static_cast<uint32_t>(i / p.nstage) & 1u;
-        mbar_wait(in_empty(st), ph ^ 1u);
-        const uint32_t q_s = base + st * L.stage_bytes;
-        const uint32_t k_s = q_s + TILE_BYTES;
-        const uint32_t v_s = k_s + L.kv_bytes;
-        mbar_expect_tx(in_full(st), L.stage_bytes);
-        tma_load_3d(q_s, &tmQ, in_full(st), h * DH, qt * TQ, b);
-        tma_load_3d(k_s, &tmK, in_full(st), h * DH, 0, b);
-        tma_load_3d(v_s, &tmV, in_full(st), h * DH, 0, b);
-        ATTN_DBG(0, i);
+  if (warp >= 8 && warp < 12) {
+    // ======================= warpgroup 2: TMA producer, S issuer, PV issuer =======================
+    reg_dec<40>();
+    if (warp == 8) {
+      if (lane == 0) {
+        for (int i = 0; i < my_tiles; ++i) {
+          const int tile = blockIdx.x + i * gridDim.x;
+          const int qt = tile % p.QT;
+          const int bh = tile / p.QT;
+          const int h = bh % p.H, b = bh / p.H;
+          const int st = i % p.nstage;
+          const uint32_t ph = static_cast<uint32_t>(i / p.nstage) & 1u;
+          mbar_wait(in_empty(st), ph ^ 1u);
+          const uint32_t q_s = base + st * L.stage_bytes;
+          const uint32_t k_s = q_s + TILE_BYTES;
+          const uint32_t v_s = k_s + L.kv_bytes;
+          mbar_expect_tx(in_full(st), L.stage_bytes);
+          tma_load_3d(q_s, &tmQ, in_full(st), h * DH, qt * TQ, b);
+          tma_load_3d(k_s, &tmK, in_full(st), h * DH, 0, b);
+          tma_load_3d(v_s, &tmV, in_full(st), h * DH, 0, b);
+          ATTN_DBG(0, i);
+        }
       }
-    }
-  } else if (warp == 9) {
-    // ---------------- S = Q K^T issuer ----------------
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, p.NKP, 0, 0);   // both operands K-major
-      for (int i = 0; i < my_tiles; ++i) {
-        const int st = i % p.nstage, bf = i % p.nbuf;
-        mbar_wait(in_full(st), static_cast<uint32_t>(i / p.nstage) & 1u);
-        mbar_wait(s_empty(bf), (static_cast<uint32_t>(i / p.nbuf) & 1u) ^ 1u);
-        tc_fence_after();
-        ATTN_DBG(1, i);
-        const uint32_t q_s = base + st * L.stage_bytes;
-        const uint32_t k_s = q_s + TILE_BYTES;
-        const uint32_t d = tmem_base + bf * p.NKP;
+    } else if (warp == 9) {
+      // ---------------- S = Q K^T issuer ----------------
+      if (lane == 0) {
+        const uint32_t idesc_s = umma_idesc_bf16(128, p.NKP, 0, 0);   // both operands K-major
+        for (int i = 0; i < my_tiles; ++i) {
+          const int st = i % p.nstage, bf = i % p.nbuf;
+          mbar_wait(in_full(st), static_cast<uint32_t>(i / p.nstage) & 1u);
+          mbar_wait(s_empty(bf), (static_cast<uint32_t>(i / p.nbuf) & 1u) ^ 1u);
+          tc_fence_after();
+          ATTN_DBG(1, i);
+          const uint32_t q_s = base + st * L.stage_bytes;
+          const uint32_t k_s = q_s + TILE_BYTES;
+          const uint32_t d = tmem_base + bf * p.NKP;
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) {
-          umma_bf16_ss(d, umma_smem_desc_sw128(q_s + k * 32, 16, 1024),
-                       umma_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < DH / 16; ++k) {
+            umma_bf16_ss(d, umma_smem_desc_sw128(q_s + k * 32, 16, 1024),
+                         umma_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(s_full(bf));
+          ATTN_DBG(2, i);
         }
-        umma_commit(s_full(bf));
-        ATTN_DBG(2, i);
+      }
+    } else if (warp == 10) {
+      // ---------------- O = P V issuer (its own thread: never blocked behind a TMA wait) --------
+      if (lane == 0) {
+        const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);      // V is MN-major
+        const int ksteps = p.NKP / 16;
+        for (int i = 0; i < my_tiles; ++i) {
+          const int st = i % p.nstage;
+          mbar_wait(p_full, static_cast<uint32_t>(i) & 1u);
+          mbar_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+          tc_fence_after();
+          ATTN_DBG(7, i);
+          const uint32_t v_s = base + st * L.stage_bytes + TILE_BYTES + L.kv_bytes;
+          const uint32_t p_s = base + L.p_off;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint64_t ad = umma_smem_desc_sw128(p_s + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024);
+            const uint64_t bd = umma_smem_desc_sw128(v_s + j * 2048, 8192, 1024);
+            umma_bf16_ss(tmem_base + O_COL, ad, bd, idesc_o, j > 0 ? 1u : 0u);
+          }
+          umma_commit(o_full);
+          umma_commit(p_empty);
+          ATTN_DBG(8, i);
+          umma_commit(in_empty(st));   // Q/K were consumed by S(i) long before (softmax(i) waited on it)
+        }
       }
     }
-  } else if (warp == 10) {
-    // ---------------- O = P V issuer ----------------
-    // A separate thread from the S issuer: waiting for the NEXT tile's TMA must never delay
-    // this tile's P V product.
-    if (lane == 0) {
-      const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);      // V is MN-major
-      const int ksteps = p.NKP / 16;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int st = i % p.nstage;
-        mbar_wait(p_full, static_cast<uint32_t>(i) & 1u);
-        mbar_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
-        tc_fence_after();
-        ATTN_DBG(7, i);
-        const uint32_t v_s = base + st * L.stage_bytes + TILE_BYTES + L.kv_bytes;
-        const uint32_t p_s = base + L.p_off;
-        for (int j = 0; j < ksteps; ++j) {
-          const uint64_t ad = umma_smem_desc_sw128(p_s + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_smem_desc_sw128(v_s + j * 2048, 8192, 1024);
-          umma_bf16_ss(tmem_base + O_COL, ad, bd, idesc_o, j > 0 ? 1u : 0u);
-        }
-        umma_commit(o_full);
-        umma_commit(p_empty);
-        ATTN_DBG(8, i);
-        umma_commit(in_empty(st));   // Q/K were consumed by S(i) long before (softmax(i) waited on it)
+  } else if (warp >= 12) {
+    // ======================= warpgroup 3: O epilogue =======================
+    // TMEM -> registers -> (1/rowsum) -> bf16 -> swizzled smem -> TMA store, concurrently with the
+    // softmax warps working on the next tile.
+    reg_dec<96>();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int etid = threadIdx.x - 384;     // 0..127
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t o_s = base + L.o_off;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int qt = tile % p.QT;
+      const int bh = tile / p.QT;
+      const int h = bh % p.H, b = bh / p.H;
+      mbar_wait(o_full, static_cast<uint32_t>(i) & 1u);
+      tc_fence_after();
+      if (etid == 0) ATTN_DBG(9, i);
+      uint32_t ov[64];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL, *reinterpret_cast<uint32_t(*)[32]>(&ov[0]));
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + 32, *reinterpret_cast<uint32_t(*)[32]>(&ov[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      mbar_wait(inv_full(i & 1), static_cast<uint32_t>(i >> 1) & 1u);
+      const float inv = xch[512 + (i & 1) * 128 + row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(inv_empty(i & 1));
+      if (etid == 0) tma_store_wait_read<0>();
+      named_bar_sync(3, 128);
+      if (etid == 0) ATTN_DBG(10, i);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t addr = o_s + row * 128 + ((static_cast<uint32_t>(g) ^ sw) << 4);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(ov[g * 8 + j]) * inv;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                     "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])),
+                     "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+      }
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (etid == 0) {
+        tma_store_3d(&tmO, o_s, h * DH, qt * TQ, b);
+        tma_store_commit();
+        ATTN_DBG(11, i);
       }
     }
-  } else if (warp < 8) {
-    // ---------------- softmax + epilogue (8 warps) ----------------
-    // Software-pipelined: softmax(i+1) runs before epilogue(i), so the P V product of tile i
-    // and its TMEM->HBM write-out overlap the exponentials of tile i+1.
+    if (etid == 0) tma_store_wait<0>();
+  } else {
+    // ======================= warpgroups 0,1: softmax =======================
+    reg_inc<184>();
     const int quarter = warp & 3, hf = warp >> 2;
     const int row = quarter * 32 + lane;
     const int tid = threadIdx.x;            // 0..255
@@ -199,10 +280,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int nunits = half_cols >> 3;      // <= 16
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t p_s = base + L.p_off;
-    const uint32_t o_s = base + L.o_off;
-
-    // returns (1/sum, lse) of this thread's row for tile i
-    auto softmax = [&](int i, float& inv_out, float& lse_out) {
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int qt = tile % p.QT;
+      const int bh = tile / p.QT;
       const int bf = i % p.nbuf;
       mbar_wait(s_full(bf), static_cast<uint32_t>(i / p.nbuf) & 1u);
       tc_fence_after();
@@ -249,11 +330,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int u = 0; u < 16; ++u) {
         if (u < nunits) {
           float e[8];
+          // alternate units between the MUFU and the FMA-pipe exponential
+          if (u & 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            e[j] = exp2f(__uint_as_float(sv[u][j]) - mx);
-            sum += e[j];
+            for (int j = 0; j < 8; ++j) e[j] = ex2_poly(__uint_as_float(sv[u][j]) - mx);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = ex2_mufu(__uint_as_float(sv[u][j]) - mx);
           }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sum += e[j];
           // packed in place: sv[u][0..3] now hold the 8 bf16 probabilities of this unit
           sv[u][0] = pack_bf16(e[0], e[1]); sv[u][1] = pack_bf16(e[2], e[3]);
           sv[u][2] = pack_bf16(e[4], e[5]); sv[u][3] = pack_bf16(e[6], e[7]);
@@ -279,60 +365,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (tid == 0) ATTN_DBG(6, i);
       named_bar_sync(2, 256);
       sum += xch[256 + (hf ^ 1) * 128 + row];
-      inv_out = 1.0f / sum;
-      lse_out = (mx + log2f(sum)) * LN2;
-    };
-
-    auto epilogue = [&](int i, float inv, float lse_val) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      const int qt = tile % p.QT;
-      const int bh = tile / p.QT;
-      const int h = bh % p.H, b = bh / p.H;
-      mbar_wait(o_full, static_cast<uint32_t>(i) & 1u);
-      tc_fence_after();
-      if (tid == 0) ATTN_DBG(9, i);
-      uint32_t ov[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + hf * 32, ov);
-      tmem_ld_wait();
-      tc_fence_before();
+      // hand 1/rowsum to the epilogue warpgroup (double-buffered slot) and write the log-sum-exp
+      mbar_wait(inv_empty(i & 1), (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
+      if (hf == 0) {
+        xch[512 + (i & 1) * 128 + row] = 1.0f / sum;
+        const int qrow = qt * TQ + row;
+        if (qrow < p.Nq && p.lse != nullptr)
+          p.lse[static_cast<int64_t>(bh) * p.Nq + qrow] = (mx + log2f(sum)) * LN2;
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
-      if (tid == 0) tma_store_wait_read<0>();
-      named_bar_sync(2, 256);
-      if (tid == 0) ATTN_DBG(10, i);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
-        const uint32_t addr = o_s + row * 128 + ((piece ^ sw) << 4);
-        float f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(ov[g * 8 + j]) * inv;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                     "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])),
-                     "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
-      }
-      const int qrow = qt * TQ + row;
-      if (hf == 0 && qrow < p.Nq && p.lse != nullptr)
-        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Nq + qrow] = lse_val;
-      fence_proxy_async();
-      named_bar_sync(2, 256);
-      if (tid == 0) {
-        tma_store_3d(&tmO, o_s, h * DH, qt * TQ, b);
-        tma_store_commit();
-        ATTN_DBG(11, i);
-      }
-    };
-
-    float inv_cur = 0.f, lse_cur = 0.f;
-    if (my_tiles > 0) softmax(0, inv_cur, lse_cur);
-    for (int i = 0; i < my_tiles; ++i) {
-      float inv_nxt = 0.f, lse_nxt = 0.f;
-      if (i + 1 < my_tiles) softmax(i + 1, inv_nxt, lse_nxt);
-      epilogue(i, inv_cur, lse_cur);
-      inv_cur = inv_nxt;
-      lse_cur = lse_nxt;
+      if (lane == 0) mbar_arrive(inv_full(i & 1));
     }
-    if (tid == 0) tma_store_wait<0>();
   }
   __syncwarp();
   tc_fence_before();
@@ -556,7 +599,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               const int kcol = kt * TQ + hf * 64 + j;
               const bool ok = row_ok && (kcol < p.Nk);
               const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
-              pe[j] = ok ? exp2f(sj * p.scale_log2 - l2) : 0.f;
+              // exponentials alternate between MUFU and the FMA-pipe polynomial (see ex2_poly)
+              const float xa = sj * p.scale_log2 - l2;
+              pe[j] = ok ? ((j & 2) ? ex2_poly(xa) : ex2_mufu(xa)) : 0.f;
             }
           }
           mbar_wait(pds_empty, pp ^ 1u);
