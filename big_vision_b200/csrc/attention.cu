@@ -101,6 +101,136 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
 }
 
+
+// Everything the softmax warpgroups need, copied into registers once (kernel parameters live in
+// constant memory; re-reading them inside the unrolled per-unit code costs an LDCU round trip each
+// time and was the dominant stall of the first version).
+struct SoftmaxCtx {
+  uint32_t tmem_base, p_s, bar, s_full0, s_empty0, p_full, p_empty, inv_full0, inv_empty0;
+  float* xch;
+  float* lse;
+  long long* dbg;
+  int my_tiles, NKP, Nk, Nq, QT, nbuf;
+  float scale_log2;
+};
+
+#define SM_DBG(ev, i)                                                         \
+  do {                                                                        \
+    if (c.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (i) < 32)  \
+      c.dbg[(i) * 16 + (ev)] = clock64();                                     \
+  } while (0)
+
+// NU = number of 8-column units per thread (compile time; 0 = run time, up to 16)
+template <int NU>
+__device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, hf = warp >> 2;
+  const int row = quarter * 32 + lane;
+  const uint32_t sw = static_cast<uint32_t>(row & 7);
+  const int nunits = NU ? NU : (c.NKP >> 4);
+  const int half_cols = nunits * 8;
+  const int kbase = hf * nunits;                    // first 8-column unit of this warp's half
+  const int valid = c.Nk - hf * half_cols;          // columns of this half that are real keys
+  const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+  const uint32_t p_row = c.p_s + row * 128;
+  const float scale_log2 = c.scale_log2;
+  float* xch = c.xch;
+  const int nbuf = c.nbuf, NKP = c.NKP, QT = c.QT, Nq = c.Nq;
+#define UNIT_ON(u) (NU ? ((u) < NU) : ((u) < nunits))
+  for (int i = 0; i < c.my_tiles; ++i) {
+    const int tile = blockIdx.x + i * gridDim.x;
+    const int qt = tile % QT;
+    const int bh = tile / QT;
+    const int bf = i % nbuf;
+    mbar_wait(c.s_full0 + 8u * bf, static_cast<uint32_t>(i / nbuf) & 1u);
+    tc_fence_after();
+    SM_DBG(3, i);
+    uint32_t sv[16][8];
+    const uint32_t s_addr = c.tmem_base + lane_addr + bf * NKP + hf * half_cols;
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (UNIT_ON(u)) tmem_ld_x8(s_addr + u * 8, sv[u]);
+    tmem_ld_wait();
+    SM_DBG(12, i);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.s_empty0 + 8u * bf);
+
+    // row maximum of the raw scores (scale > 0, so max commutes with the scaling)
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (UNIT_ON(u)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float sc = __uint_as_float(sv[u][j]);
+          if (u * 8 + j >= valid) sc = -INFINITY;     // padded key columns
+          sv[u][j] = __float_as_uint(sc);
+          mx = fmaxf(mx, sc);
+        }
+      }
+    }
+    xch[hf * 128 + row] = mx;
+    SM_DBG(13, i);
+    named_bar_sync(2, 256);
+    mx = fmaxf(mx, xch[(hf ^ 1) * 128 + row]);
+    SM_DBG(4, i);
+    const float mxs = mx * scale_log2;
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (UNIT_ON(u)) {
+        float e[8];
+        // exp2(scale * s - scale * max); units alternate between MUFU and the FMA-pipe polynomial
+        if (u & 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = ex2_poly(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = ex2_mufu(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += e[j];
+        // packed in place: sv[u][0..3] now hold the 8 bf16 probabilities of this unit
+        sv[u][0] = pack_bf16(e[0], e[1]); sv[u][1] = pack_bf16(e[2], e[3]);
+        sv[u][2] = pack_bf16(e[4], e[5]); sv[u][3] = pack_bf16(e[6], e[7]);
+      }
+    }
+    SM_DBG(14, i);
+    // the P buffer is free once the previous tile's P V product has retired
+    mbar_wait(c.p_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
+    SM_DBG(5, i);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (UNIT_ON(u)) {
+        const uint32_t k = static_cast<uint32_t>(kbase + u);      // global 8-column unit index
+        const uint32_t addr = p_row + (k >> 3) * TILE_BYTES + (((k & 7u) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sv[u][0]),
+                     "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
+      }
+    }
+    xch[256 + hf * 128 + row] = sum;
+    SM_DBG(15, i);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.p_full);
+    SM_DBG(6, i);
+    named_bar_sync(2, 256);
+    sum += xch[256 + (hf ^ 1) * 128 + row];
+    // hand 1/rowsum to the epilogue warpgroup (double-buffered slot) and write the log-sum-exp
+    mbar_wait(c.inv_empty0 + 8u * (i & 1), (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
+    if (hf == 0) {
+      xch[512 + (i & 1) * 128 + row] = 1.0f / sum;
+      const int qrow = qt * TQ + row;
+      if (qrow < Nq && c.lse != nullptr)
+        c.lse[static_cast<int64_t>(bh) * Nq + qrow] = (mxs + log2f(sum)) * LN2;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.inv_full0 + 8u * (i & 1));
+  }
+#undef UNIT_ON
+}
+
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -272,110 +402,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else {
     // ======================= warpgroups 0,1: softmax =======================
     reg_inc<184>();
-    const int quarter = warp & 3, hf = warp >> 2;
-    const int row = quarter * 32 + lane;
-    const int tid = threadIdx.x;            // 0..255
-    const uint32_t sw = static_cast<uint32_t>(row & 7);
-    const int half_cols = p.NKP >> 1;       // multiple of 8
-    const int nunits = half_cols >> 3;      // <= 16
-    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t p_s = base + L.p_off;
-    for (int i = 0; i < my_tiles; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
-      const int qt = tile % p.QT;
-      const int bh = tile / p.QT;
-      const int bf = i % p.nbuf;
-      mbar_wait(s_full(bf), static_cast<uint32_t>(i / p.nbuf) & 1u);
-      tc_fence_after();
-      if (tid == 0) ATTN_DBG(3, i);
-      uint32_t sv[16][8];
-      const uint32_t s_addr = tmem_base + lane_addr + bf * p.NKP + hf * half_cols;
-#pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (u < nunits) tmem_ld_x8(s_addr + u * 8, sv[u]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(bf));
-
-      float mx = -INFINITY;
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        if (u < nunits) {
-          const int c0 = hf * half_cols + u * 8;
-          if (c0 + 8 <= p.Nk) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float sc = __uint_as_float(sv[u][j]) * p.scale_log2;
-              sv[u][j] = __float_as_uint(sc);
-              mx = fmaxf(mx, sc);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float sc = __uint_as_float(sv[u][j]) * p.scale_log2;
-              sc = (c0 + j < p.Nk) ? sc : -INFINITY;
-              sv[u][j] = __float_as_uint(sc);
-              mx = fmaxf(mx, sc);
-            }
-          }
-        }
-      }
-      xch[hf * 128 + row] = mx;
-      named_bar_sync(2, 256);
-      mx = fmaxf(mx, xch[(hf ^ 1) * 128 + row]);
-      if (tid == 0) ATTN_DBG(4, i);
-      float sum = 0.f;
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        if (u < nunits) {
-          float e[8];
-          // alternate units between the MUFU and the FMA-pipe exponential
-          if (u & 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = ex2_poly(__uint_as_float(sv[u][j]) - mx);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = ex2_mufu(__uint_as_float(sv[u][j]) - mx);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sum += e[j];
-          // packed in place: sv[u][0..3] now hold the 8 bf16 probabilities of this unit
-          sv[u][0] = pack_bf16(e[0], e[1]); sv[u][1] = pack_bf16(e[2], e[3]);
-          sv[u][2] = pack_bf16(e[4], e[5]); sv[u][3] = pack_bf16(e[6], e[7]);
-        }
-      }
-      // the P buffer is free once the previous tile's P V product has retired
-      mbar_wait(p_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
-      if (tid == 0) ATTN_DBG(5, i);
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        if (u < nunits) {
-          const int c0 = hf * half_cols + u * 8;
-          const uint32_t addr = p_s + (c0 >> 6) * TILE_BYTES + row * 128 +
-                                ((static_cast<uint32_t>((c0 & 63) >> 3) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sv[u][0]),
-                       "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
-        }
-      }
-      xch[256 + hf * 128 + row] = sum;
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      if (tid == 0) ATTN_DBG(6, i);
-      named_bar_sync(2, 256);
-      sum += xch[256 + (hf ^ 1) * 128 + row];
-      // hand 1/rowsum to the epilogue warpgroup (double-buffered slot) and write the log-sum-exp
-      mbar_wait(inv_empty(i & 1), (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
-      if (hf == 0) {
-        xch[512 + (i & 1) * 128 + row] = 1.0f / sum;
-        const int qrow = qt * TQ + row;
-        if (qrow < p.Nq && p.lse != nullptr)
-          p.lse[static_cast<int64_t>(bh) * p.Nq + qrow] = (mx + log2f(sum)) * LN2;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(inv_full(i & 1));
-    }
+    SoftmaxCtx c;
+    c.tmem_base = tmem_base; c.p_s = base + L.p_off; c.xch = xch; c.bar = bar; c.my_tiles = my_tiles;
+    c.s_full0 = s_full(0); c.s_empty0 = s_empty(0); c.p_full = p_full; c.p_empty = p_empty;
+    c.inv_full0 = inv_full(0); c.inv_empty0 = inv_empty(0);
+    c.NKP = p.NKP; c.Nk = p.Nk; c.Nq = p.Nq; c.QT = p.QT; c.nbuf = p.nbuf; c.scale_log2 = p.scale_log2;
+    c.lse = p.lse; c.dbg = p.dbg;
+    const int nunits = p.NKP >> 4;
+    if (nunits == 13) softmax_warpgroups<13>(c);
+    else if (nunits == 4) softmax_warpgroups<4>(c);
+    else if (nunits == 16) softmax_warpgroups<16>(c);
+    else softmax_warpgroups<0>(c);
   }
   __syncwarp();
   tc_fence_before();

@@ -285,12 +285,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t flush = 0;
-    const bool unit_alpha = (p.alpha == 1.0f);
+    // kernel parameters used per element are copied to registers once (constant-bank reads inside
+    // the unrolled column loop would put an LDCU round trip on every group's dependency chain)
+    const int pM = p.M, pN = p.N, p_mod = p.aux_row_mod, p_reduce = p.reduce_out;
+    const float p_alpha = p.alpha;
+    const float* __restrict__ p_bias = p.bias;
+    const bf16* __restrict__ p_aux = p.aux;
+    const long long p_ldaux = p.ldaux;
+    const bool unit_alpha = (p_alpha == 1.0f);
     for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
       int m0, n0, kb0, kb1;
       decode_tile(tile, m0, n0, kb0, kb1);
       const int grow = m0 + row;
-      const bool row_ok = grow < p.M;
+      const bool row_ok = grow < pM;
       // The residual / pre-activation operand of this thread's row for the WHOLE tile is fetched
       // before waiting for the accumulator, so its HBM/L2 latency hides behind the mainloop.
       constexpr bool HAS_AUX = (EF == EF_RESID || EF == EF_DGELU);
@@ -299,8 +306,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (HAS_AUX) {
         const bf16* aux_row = nullptr;
         if (row_ok) {
-          long long ar = p.aux_row_mod > 0 ? (grow % p.aux_row_mod) : grow;
-          aux_row = p.aux + ar * p.ldaux;
+          long long ar = p_mod > 0 ? (grow % p_mod) : grow;
+          aux_row = p_aux + ar * p_ldaux;
         }
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
@@ -308,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int g = 0; g < WC / 8; ++g) {
             const int nc = n0 + c * CH + half * WC + g * 8;
             aq_all[c * (WC / 8) + g] = make_uint4(0u, 0u, 0u, 0u);
-            if (aux_row != nullptr && nc < p.N)
+            if (aux_row != nullptr && nc < pN)
               aq_all[c * (WC / 8) + g] = *reinterpret_cast<const uint4*>(aux_row + nc);
           }
         }
@@ -347,12 +354,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
           if (!unit_alpha) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+            for (int i = 0; i < 8; ++i) v[i] *= p_alpha;
           }
-          const bool col_ok = nc < p.N;
-          if (p.bias != nullptr && col_ok) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nc + 4));
+          const bool col_ok = nc < pN;
+          if (p_bias != nullptr && col_ok) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p_bias + nc));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p_bias + nc + 4));
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
@@ -401,8 +408,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         named_bar_sync(1, EPI_THREADS);
         if (ep_tid == 0) {
           const int c0 = n0 + c * CH;
-          if (c0 < p.N) {
-            if (p.reduce_out) tma_reduce_add_2d(&tmD, buf, c0, m0);
+          if (c0 < pN) {
+            if (p_reduce) tma_reduce_add_2d(&tmD, buf, c0, m0);
             else tma_store_2d(&tmD, buf, c0, m0);
             if (DUAL) tma_store_2d(&tmD2, buf + OUT_BUF_BYTES, c0, m0);
           }

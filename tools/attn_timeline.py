@@ -15,7 +15,8 @@ from big_vision_b200 import lib as L  # noqa: E402
 from big_vision_b200 import ops  # noqa: E402
 
 EV = ["tma_issued", "S_in_ready", "S_committed", "sm_s_full", "sm_max_done", "sm_p_empty",
-      "sm_p_full_arr", "PV_ready", "PV_committed", "ep_o_full", "ep_stage_free", "ep_store"]
+      "sm_p_full_arr", "PV_ready", "PV_committed", "ep_o_full", "ep_stage_free", "ep_store",
+      "sm_ld_done", "sm_max_local", "sm_exp_done", "sm_sts_done"]
 
 
 def main():
@@ -44,7 +45,7 @@ def main():
   vals = [buf[i] for i in range(n)]
   base = min(x for x in vals if x > 0)
   print("tile " + " ".join(f"{e[:11]:>11s}" for e in EV))
-  for i in range(14):
+  for i in range(4, 12):
     row = vals[i * 16:(i + 1) * 16]
     print(f"{i:4d} " + " ".join(f"{(x - base) if x else -1:11d}" for x in row[:len(EV)]))
 
