@@ -588,9 +588,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t pair_cnt = 0, kt_cnt = 0;
+    // kernel parameters copied to registers once (see SoftmaxCtx)
+    const int pH = p.H, pNq = p.Nq, pNk = p.Nk, pQT = p.QT, pKT = p.KT;
+    const float p_scale = p.scale, p_scale_log2 = p.scale_log2;
+    const float* __restrict__ p_lse = p.lse;
     for (int it = 0; it < my_items; ++it) {
       const int bh = blockIdx.x + it * gridDim.x;
-      const int h = bh % p.H, b = bh / p.H;
+      const int h = bh % pH, b = bh / pH;
       const uint32_t ph = static_cast<uint32_t>(it) & 1u;
       // ---- prologue: delta = rowsum(O o dO), lse in log2 units
       mbar_wait(o_in_full, ph);
@@ -611,19 +615,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           acc += bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
         }
         delta_s[r] = acc;
-        lse2_s[r] = (r < p.Nq) ? p.lse[static_cast<int64_t>(bh) * p.Nq + r] * LOG2E : INFINITY;
+        lse2_s[r] = (r < pNq) ? p_lse[static_cast<int64_t>(bh) * pNq + r] * LOG2E : INFINITY;
       }
       named_bar_sync(2, 256);
       __syncwarp();
       if (lane == 0) mbar_arrive(stat_ready);
 
-      for (int kt = 0; kt < p.KT; ++kt) {
-        for (int qt = 0; qt < p.QT; ++qt, ++pair_cnt) {
+      for (int kt = 0; kt < pKT; ++kt) {
+        for (int qt = 0; qt < pQT; ++qt, ++pair_cnt) {
           const uint32_t pp = pair_cnt & 1u;
           mbar_wait(sdp_full, pp);
           tc_fence_after();
           const int qrow = qt * TQ + row;
-          const bool row_ok = qrow < p.Nq;
+          const bool row_ok = qrow < pNq;
           const float l2 = lse2_s[qrow], dl = delta_s[qrow];
           float pe[64];
           {
@@ -634,10 +638,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
               const int kcol = kt * TQ + hf * 64 + j;
-              const bool ok = row_ok && (kcol < p.Nk);
+              const bool ok = row_ok && (kcol < pNk);
               const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
               // exponentials alternate between MUFU and the FMA-pipe polynomial (see ex2_poly)
-              const float xa = sj * p.scale_log2 - l2;
+              const float xa = sj * p_scale_log2 - l2;
               pe[j] = ok ? ((j & 2) ? ex2_poly(xa) : ex2_mufu(xa)) : 0.f;
             }
           }
@@ -659,8 +663,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
               for (int j2 = 0; j2 < 4; ++j2) {
                 const int j = u * 8 + j2 * 2;
-                const float d0 = p.scale * pe[j] * (__uint_as_float(dv[(j & 31)]) - dl);
-                const float d1 = p.scale * pe[j + 1] * (__uint_as_float(dv[(j & 31) + 1]) - dl);
+                const float d0 = p_scale * pe[j] * (__uint_as_float(dv[(j & 31)]) - dl);
+                const float d1 = p_scale * pe[j + 1] * (__uint_as_float(dv[(j & 31) + 1]) - dl);
                 pk[j2] = pack_bf16(pe[j], pe[j + 1]);
                 dk[j2] = pack_bf16(pe[j] != 0.f ? d0 : 0.f, pe[j + 1] != 0.f ? d1 : 0.f);
               }
@@ -673,7 +677,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_full);
 
-          if (qt == p.QT - 1) {
+          if (qt == pQT - 1) {
             // ---- dV_kt, dK_kt complete: TMEM -> bf16 -> staging -> TMA store (rows = keys)
             mbar_wait(dkv_full, kt_cnt & 1u);
             tc_fence_after();
@@ -712,11 +716,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ---- dQ tiles complete
       mbar_wait(dq_full, ph);
       tc_fence_after();
-      for (int qt = 0; qt < p.QT; ++qt) {
+      for (int qt = 0; qt < pQT; ++qt) {
         uint32_t a[32];
         tmem_ld_32x32b_x32(tmem_base + lane_addr + DQ_COL + qt * DH + hf * 32, a);
         tmem_ld_wait();
-        if (qt == p.QT - 1) {
+        if (qt == pQT - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(dq_empty);
