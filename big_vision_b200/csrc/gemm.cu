@@ -37,14 +37,17 @@ constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int OUT_BUF_BYTES = BM * 128;      // 128 rows x 128 B
-constexpr int NUM_THREADS = 320;
-constexpr int EPI_WARPS = 8;
+// epilogue warps: EPI_PARTS warps per TMEM lane quarter, each taking 1/EPI_PARTS of the columns
+// of every staging chunk (more warps = more MUFU / FMA latency hiding in the gelu epilogues)
+constexpr int EPI_PARTS = 2;
+constexpr int EPI_WARPS = 4 * EPI_PARTS;
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 
 // epilogue families (template parameter)
 enum : int { EF_BIAS = 0, EF_GELU = 1, EF_RESID = 2, EF_DGELU = 3 };
 
-template <int BN, int CTAS, bool DUAL_OUT>
+template <int BN, int CTAS, bool DUAL_OUT, bool AUX_TMA>
 struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;                 // rows of B this CTA loads
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
@@ -52,11 +55,14 @@ struct Cfg {
   // staging buffers for the TMA stores: 2 (double-buffered), or 2 x 2 when the epilogue
   // writes two tensors (gelu output + pre-activation)
   static constexpr int OUT_BUFS = DUAL_OUT ? 4 : 2;
+  // ring of TMA-loaded tiles of the epilogue's second operand (residual / gelu pre-activation)
+  static constexpr int AUX_BUFS = AUX_TMA ? 3 : 0;
   static constexpr int SMEM_LIMIT = 232448 - 1280;         // 227 KB minus barriers / align slack
-  static constexpr int STAGES_FIT = (SMEM_LIMIT - OUT_BUFS * OUT_BUF_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - (OUT_BUFS + AUX_BUFS) * OUT_BUF_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256 (power of two)
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + OUT_BUFS * OUT_BUF_BYTES;
+  static constexpr int AUX_OFFSET = STAGES * STAGE_BYTES + OUT_BUFS * OUT_BUF_BYTES;
+  static constexpr int BAR_OFFSET = AUX_OFFSET + AUX_BUFS * OUT_BUF_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
 };
 
@@ -88,8 +94,9 @@ __device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t cta) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
+  // default (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive(cta_id): the explicit
+  // .release.cluster form costs a MEMBAR.ALL + ERRBAR per arrival (6% of the gelu GEMM's samples)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion may be signalled on the CTA-pair leader's mbarrier.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar,
@@ -117,12 +124,14 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
 }
 
-template <int BN, bool OUT_F32, int EF, int CTAS>
+// AUXM: how the epilogue's second operand arrives: 0 none, 1 per-thread global loads (row-modulo
+// position embeddings, fp32 outputs), 2 TMA ring in shared memory (residual / gelu' operands)
+template <int BN, bool OUT_F32, int EF, int CTAS, int AUXM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
-            const GemmDev p) {
-  using C = Cfg<BN, CTAS, EF == EF_GELU>;
+            const __grid_constant__ CUtensorMap tmAux, const GemmDev p) {
+  using C = Cfg<BN, CTAS, EF == EF_GELU, AUXM == 2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -135,6 +144,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  auto aux_full = [&](int b) { return bar_base + 8u * (2 * C::STAGES + 5 + b); };
+  const uint32_t aux_buf0 = base + C::AUX_OFFSET;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(base_ptr + C::BAR_OFFSET + 8 * (2 * C::STAGES + 4));
 
@@ -148,10 +159,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
     if (EF == EF_GELU) tma_prefetch_desc(&tmD2);
+    if (AUXM == 2) tma_prefetch_desc(&tmAux);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
+    for (int b = 0; b < 3; ++b) mbar_init(aux_full(b), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EPI_WARPS * CTAS);   // one arrive per epilogue warp of each CTA
@@ -275,12 +288,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ========================= epilogue (8 warps, every CTA) =========================
     const int ep_tid = threadIdx.x - 64;
     const int quarter = warp_idx & 3;               // TMEM lanes this warp may access
-    const int half = (warp_idx - 2) >> 2;           // which half of each staging chunk's columns
+    const int half = (warp_idx - 2) >> 2;           // which column part of each staging chunk
     const int row = quarter * 32 + lane;            // row within this CTA's tile == TMEM lane
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     constexpr bool DUAL = (EF == EF_GELU);
     constexpr int CH = OUT_F32 ? 32 : 64;           // columns per staging chunk / TMA store
-    constexpr int WC = CH / 2;                      // columns per warp per chunk (16 or 32)
+    constexpr int WC = CH / EPI_PARTS;              // columns per warp per chunk
     constexpr int NCHUNK = BN / CH;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -293,17 +306,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bf16* __restrict__ p_aux = p.aux;
     const long long p_ldaux = p.ldaux;
     const bool unit_alpha = (p_alpha == 1.0f);
+    constexpr bool HAS_AUX = (EF == EF_RESID || EF == EF_DGELU);
+    static_assert(!(AUXM == 2) || (HAS_AUX && !OUT_F32), "TMA aux ring is for bf16 residual/gelu' tiles");
+    static_assert(HAS_AUX == (AUXM != 0), "aux mode must match the epilogue family");
+    // --- TMA aux ring (AUXM == 2): chunk q of this CTA's epilogue stream lives in buffer q % 3;
+    // thread 0 keeps two chunks in flight ahead of the one being consumed.
+    uint32_t aux_q = 0;                    // chunks consumed so far
+    auto aux_issue = [&](uint32_t q) {     // called by ep_tid 0 only
+      const uint32_t t_iter = q / NCHUNK, c = q % NCHUNK;
+      const int tile = tile_start + static_cast<int>(t_iter) * tile_step;
+      if (tile >= p.total_tiles) return;
+      int m0, n0, kb0, kb1;
+      decode_tile(tile, m0, n0, kb0, kb1);
+      const uint32_t b = q % 3u;
+      mbar_expect_tx(aux_full(b), OUT_BUF_BYTES);
+      tma_load_2d(aux_buf0 + b * OUT_BUF_BYTES, &tmAux, aux_full(b), n0 + static_cast<int>(c) * CH, m0);
+    };
+    if (AUXM == 2 && ep_tid == 0) { aux_issue(0); aux_issue(1); }
     for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
       int m0, n0, kb0, kb1;
       decode_tile(tile, m0, n0, kb0, kb1);
       const int grow = m0 + row;
       const bool row_ok = grow < pM;
-      // The residual / pre-activation operand of this thread's row for the WHOLE tile is fetched
-      // before waiting for the accumulator, so its HBM/L2 latency hides behind the mainloop.
-      constexpr bool HAS_AUX = (EF == EF_RESID || EF == EF_DGELU);
-      constexpr int NAUX = HAS_AUX ? NCHUNK * (WC / 8) : 1;
+      // AUXM == 1: the residual / position-embedding operand of this thread's row for the WHOLE
+      // tile is fetched before waiting for the accumulator.
+      constexpr int NAUX = (AUXM == 1) ? NCHUNK * (WC / 8) : 1;
       uint4 aq_all[NAUX];
-      if (HAS_AUX) {
+      if (AUXM == 1) {
         const bf16* aux_row = nullptr;
         if (row_ok) {
           long long ar = p_mod > 0 ? (grow % p_mod) : grow;
@@ -331,8 +360,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int col_t = c * CH + half * WC;       // first column (within the tile) of this warp
         const int ncol0 = n0 + col_t;
         uint32_t r[WC];
-        if constexpr (OUT_F32) tmem_ld_32x32b_x16(t_row + col_t, r);
-        else tmem_ld_32x32b_x32(t_row + col_t, r);
+        if constexpr (WC == 32) tmem_ld_32x32b_x32(t_row + col_t, r);
+        else if constexpr (WC == 16) tmem_ld_32x32b_x16(t_row + col_t, r);
+        else tmem_ld_32x32b_x8(t_row + col_t, r);
         tmem_ld_wait();
         if (c == NCHUNK - 1) {
           // accumulator fully drained into registers -> hand TMEM back to the MMA warp
@@ -346,6 +376,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // make sure the TMA store that last used this staging buffer has read it
         if (ep_tid == 0) tma_store_wait_read<1>();
         named_bar_sync(1, EPI_THREADS);
+        uint32_t aux_s = 0;
+        if (AUXM == 2) {
+          // every thread is past chunk q-1 (barrier above), so its buffer can be refilled with q+2
+          if (ep_tid == 0) aux_issue(aux_q + 2);
+          mbar_wait(aux_full(aux_q % 3u), (aux_q / 3u) & 1u);
+          aux_s = aux_buf0 + (aux_q % 3u) * OUT_BUF_BYTES + row * 128;
+          ++aux_q;
+        }
 #pragma unroll
         for (int g = 0; g < WC / 8; ++g) {      // 8 columns per group
           const int nc = ncol0 + g * 8;
@@ -371,7 +409,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[i] = gelu_tanh_fast(v2[i]);
             }
           } else if (EF == EF_RESID || EF == EF_DGELU) {
-            const uint4 q = aq_all[c * (WC / 8) + g];
+            uint4 q;
+            if (AUXM == 2) {
+              const uint32_t pc = static_cast<uint32_t>(half * (WC / 8) + g);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(aux_s + ((pc ^ sw) << 4)));
+            } else {
+              q = aq_all[c * (WC / 8) + g];
+            }
             const float a[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                 bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
             if (EF == EF_RESID) {
@@ -383,7 +428,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (OUT_F32) {
-            const uint32_t p0 = static_cast<uint32_t>(half * 4 + g * 2), p1 = p0 + 1;
+            const uint32_t p0 = static_cast<uint32_t>(half * (WC / 4) + g * 2), p1 = p0 + 1;
             const uint32_t a0 = buf + row * 128 + ((p0 ^ sw) << 4);
             const uint32_t a1 = buf + row * 128 + ((p1 ^ sw) << 4);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(v[0]),
@@ -391,7 +436,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(v[4]),
                          "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
           } else {
-            const uint32_t piece = static_cast<uint32_t>(half * 4 + g);
+            const uint32_t piece = static_cast<uint32_t>(half * (WC / 8) + g);
             const uint32_t a0 = buf + row * 128 + ((piece ^ sw) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0),
                          "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
@@ -437,10 +482,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, bool OUT_F32, int EF, int CTAS>
+template <int BN, bool OUT_F32, int EF, int CTAS, int AUXM>
 int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
-  using C = Cfg<BN, CTAS, EF == EF_GELU>;
-  CUtensorMap tmA, tmB, tmD, tmD2;
+  using C = Cfg<BN, CTAS, EF == EF_GELU, AUXM == 2>;
+  CUtensorMap tmA, tmB, tmD, tmD2, tmAux;
   int rc;
   const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   if (g.a_mn) rc = make_tmap_2d(&tmA, bf, g.A, g.M, g.K, g.lda * 2, 64, 64);
@@ -453,6 +498,11 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   else         rc = make_tmap_2d(&tmD, bf, g.D, g.N, g.M, g.ldd * 2, 64, BM);
   if (rc) return rc;
   tmD2 = tmD;
+  tmAux = tmD;
+  if (AUXM == 2) {
+    rc = make_tmap_2d(&tmAux, bf, g.aux, g.N, g.M, g.ldaux * 2, 64, BM);
+    if (rc) return rc;
+  }
   if (EF == EF_GELU) {
     rc = make_tmap_2d(&tmD2, bf, g.D2, g.N, g.M, g.ldd2 * 2, 64, BM);
     if (rc) return rc;
@@ -489,7 +539,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   p.ldaux = g.ldaux;
   p.aux_row_mod = g.aux_row_mod;
 
-  auto kern = gemm_kernel<BN, OUT_F32, EF, CTAS>;
+  auto kern = gemm_kernel<BN, OUT_F32, EF, CTAS, AUXM>;
   static bool attr_set = false;
   if (!attr_set) {
     rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -510,7 +560,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmD2, p), "gemm_kernel launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmD2, tmAux, p), "gemm_kernel launch");
 }
 
 template <int BN, int CTAS>
@@ -519,14 +569,18 @@ int dispatch_epi(const GemmArgs& g, cudaStream_t s) {
   switch (g.epi) {
     case EPI_NONE:
     case EPI_BIAS:
-      return f32 ? launch_cfg<BN, true, EF_BIAS, CTAS>(g, s) : launch_cfg<BN, false, EF_BIAS, CTAS>(g, s);
+      return f32 ? launch_cfg<BN, true, EF_BIAS, CTAS, 0>(g, s) : launch_cfg<BN, false, EF_BIAS, CTAS, 0>(g, s);
     case EPI_BIAS_RESID:
-      return f32 ? launch_cfg<BN, true, EF_RESID, CTAS>(g, s) : launch_cfg<BN, false, EF_RESID, CTAS>(g, s);
+      if (f32) return launch_cfg<BN, true, EF_RESID, CTAS, 1>(g, s);
+      // plain row-aligned residual: TMA ring; row-modulo (position embedding) operand: per-thread loads
+      return g.aux_row_mod > 0 ? launch_cfg<BN, false, EF_RESID, CTAS, 1>(g, s)
+                               : launch_cfg<BN, false, EF_RESID, CTAS, 2>(g, s);
     case EPI_BIAS_GELU:
-      return launch_cfg<BN, false, EF_GELU, CTAS>(g, s);
+      return launch_cfg<BN, false, EF_GELU, CTAS, 0>(g, s);
     case EPI_DGELU:
       if (f32) { set_error("bv_gemm: DGELU epilogue writes bf16"); return BV_ERR_INVALID; }
-      return launch_cfg<BN, false, EF_DGELU, CTAS>(g, s);
+      if (g.aux_row_mod > 0) { set_error("bv_gemm: DGELU takes a row-aligned aux"); return BV_ERR_INVALID; }
+      return launch_cfg<BN, false, EF_DGELU, CTAS, 2>(g, s);
   }
   set_error("bv_gemm: bad epilogue %d", g.epi);
   return BV_ERR_INVALID;
