@@ -130,12 +130,12 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
   const int nunits = NU ? NU : (c.NKP >> 4);
   const int half_cols = nunits * 8;
   const int kbase = hf * nunits;                    // first 8-column unit of this warp's half
-  const int valid = c.Nk - hf * half_cols;          // columns of this half that are real keys
+  const int valid = pin_reg(c.Nk - hf * half_cols);  // columns of this half that are real keys
   const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
   const uint32_t p_row = c.p_s + row * 128;
-  const float scale_log2 = c.scale_log2;
-  float* xch = c.xch;
-  const int nbuf = c.nbuf, NKP = c.NKP, QT = c.QT, Nq = c.Nq;
+  const float scale_log2 = pin_reg(c.scale_log2);
+  float* xch = pin_reg(c.xch);
+  const int nbuf = pin_reg(c.nbuf), NKP = pin_reg(c.NKP), QT = pin_reg(c.QT), Nq = pin_reg(c.Nq);
 #define UNIT_ON(u) (NU ? ((u) < NU) : ((u) < nunits))
   for (int i = 0; i < c.my_tiles; ++i) {
     const int tile = blockIdx.x + i * gridDim.x;
@@ -313,11 +313,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t q_s = base + st * L.stage_bytes;
           const uint32_t k_s = q_s + TILE_BYTES;
           const uint32_t d = tmem_base + bf * p.NKP;
+          const uint64_t dq = umma_smem_desc_sw128(q_s, 16, 1024), dk = umma_smem_desc_sw128(k_s, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            umma_bf16_ss(d, umma_smem_desc_sw128(q_s + k * 32, 16, 1024),
-                         umma_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(d, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
           umma_commit(s_full(bf));
           ATTN_DBG(2, i);
         }
@@ -335,11 +333,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ATTN_DBG(7, i);
           const uint32_t v_s = base + st * L.stage_bytes + TILE_BYTES + L.kv_bytes;
           const uint32_t p_s = base + L.p_off;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint64_t ad = umma_smem_desc_sw128(p_s + (j >> 2) * TILE_BYTES + (j & 3) * 32, 16, 1024);
-            const uint64_t bd = umma_smem_desc_sw128(v_s + j * 2048, 8192, 1024);
-            umma_bf16_ss(tmem_base + O_COL, ad, bd, idesc_o, j > 0 ? 1u : 0u);
-          }
+          const uint64_t dpd = umma_smem_desc_sw128(p_s, 16, 1024), dvd = umma_smem_desc_sw128(v_s, 8192, 1024);
+          for (int j = 0; j < ksteps; ++j)
+            umma_bf16_ss(tmem_base + O_COL, dpd + (j >> 2) * (TILE_BYTES / 16) + (j & 3) * 2, dvd + j * 128,
+                         idesc_o, j > 0 ? 1u : 0u);
           umma_commit(o_full);
           umma_commit(p_empty);
           ATTN_DBG(8, i);
@@ -440,7 +437,14 @@ struct BwdDev {
   int BH, H, Nq, Nk, QT, KT;
   float scale, scale_log2;
   const float* lse;
+  long long* dbg;    // optional timeline of CTA 0 (BV_ATTN_DBG=1)
 };
+// dbg[256 + slot] : per-pair events (16 per pair, first 12 pairs) of CTA 0
+#define BWD_DBG(ev, pr)                                                       \
+  do {                                                                        \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (pr) < 12)                     \
+      p.dbg[256 + (pr) * 16 + (ev)] = clock64();                              \
+  } while (0)
 constexpr int BWD_P_OFF = 4 * OP_BYTES;                       // P  [128 x 128] bf16 (2 blocks)
 constexpr int BWD_DS_OFF = BWD_P_OFF + 2 * TILE_BYTES;        // dS [128 x 128]
 constexpr int BWD_STG_OFF = BWD_DS_OFF + 2 * TILE_BYTES;      // 16 KB output staging
@@ -508,6 +512,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_3d(q_s, &tmQ, in_full, h * DH, 0, b);
         tma_load_3d(k_s, &tmK, in_full, h * DH, 0, b);
         tma_load_3d(v_s, &tmV, in_full, h * DH, 0, b);
+        BWD_DBG(13, it * 4);
       }
     }
   } else if (warp == 9) {
@@ -526,15 +531,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
         const uint32_t va = v_s + kt * TILE_BYTES, da = do_s + qt * TILE_BYTES;
+        // descriptors are built once per tile; stepping along K only bumps the 16-byte-granular
+        // start-address field (this thread issues 32 MMAs per pair -- its instruction count matters)
+        const uint64_t dq_k = umma_smem_desc_sw128(qa, 16, 1024), dk_k = umma_smem_desc_sw128(ka, 16, 1024);
+        const uint64_t ddo_k = umma_smem_desc_sw128(da, 16, 1024), dv_k = umma_smem_desc_sw128(va, 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base + S_COL, umma_smem_desc_sw128(qa + k * 32, 16, 1024),
-                       umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_base + S_COL, dq_k + k * 2, dk_k + k * 2, id_kk, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base + DP_COL, umma_smem_desc_sw128(da + k * 32, 16, 1024),
-                       umma_smem_desc_sw128(va + k * 32, 16, 1024), id_kk, k > 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_base + DP_COL, ddo_k + k * 2, dv_k + k * 2, id_kk, k > 0 ? 1u : 0u);
         umma_commit(sdp_full);
+        BWD_DBG(5, sdp_cnt - 1);
       };
       // dV, dK, dQ contributions of pair j from the P / dS tiles the compute warps wrote
       auto issue_grads = [&](int j, uint32_t ph) {
@@ -546,23 +554,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (qt == 0) mbar_wait(dkv_empty, (kt_cnt & 1u) ^ 1u);
         if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
         tc_fence_after();
+        const uint64_t dp_mn = umma_smem_desc_sw128(p_s, TILE_BYTES, 1024);
+        const uint64_t dds_mn = umma_smem_desc_sw128(ds_s, TILE_BYTES, 1024);
+        const uint64_t dds_k = umma_smem_desc_sw128(ds_s, 16, 1024);
+        const uint64_t ddo_mn = umma_smem_desc_sw128(da, 8192, 1024);
+        const uint64_t dq_mn = umma_smem_desc_sw128(qa, 8192, 1024);
+        const uint64_t dk_mn = umma_smem_desc_sw128(ka, 8192, 1024);
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {   // contraction over 128 query rows, 16 per step
-          const uint64_t a_p = umma_smem_desc_sw128(p_s + jj * 2048, TILE_BYTES, 1024);
-          const uint64_t a_ds = umma_smem_desc_sw128(ds_s + jj * 2048, TILE_BYTES, 1024);
-          const uint64_t b_do = umma_smem_desc_sw128(da + jj * 2048, 8192, 1024);
-          const uint64_t b_q = umma_smem_desc_sw128(qa + jj * 2048, 8192, 1024);
+        for (int jj = 0; jj < 8; ++jj) {   // contraction over 128 query rows, 16 per step (2048 B)
           const uint32_t accv = (qt > 0 || jj > 0) ? 1u : 0u;
-          umma_bf16_ss(tmem_base + DV_COL, a_p, b_do, id_mm, accv);
-          umma_bf16_ss(tmem_base + DK_COL, a_ds, b_q, id_mm, accv);
+          umma_bf16_ss(tmem_base + DV_COL, dp_mn + jj * 128, ddo_mn + jj * 128, id_mm, accv);
+          umma_bf16_ss(tmem_base + DK_COL, dds_mn + jj * 128, dq_mn + jj * 128, id_mm, accv);
         }
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {   // contraction over 128 keys
-          const uint64_t a_ds = umma_smem_desc_sw128(ds_s + (jj >> 2) * TILE_BYTES + (jj & 3) * 32, 16, 1024);
-          const uint64_t b_k = umma_smem_desc_sw128(ka + jj * 2048, 8192, 1024);
-          umma_bf16_ss(tmem_base + DQ_COL + qt * DH, a_ds, b_k, id_km, (kt > 0 || jj > 0) ? 1u : 0u);
+          umma_bf16_ss(tmem_base + DQ_COL + qt * DH, dds_k + (jj >> 2) * (TILE_BYTES / 16) + (jj & 3) * 2,
+                       dk_mn + jj * 128, id_km, (kt > 0 || jj > 0) ? 1u : 0u);
         }
         umma_commit(pds_empty);
+        BWD_DBG(6, grad_cnt - 1);
         if (qt == p.QT - 1) { umma_commit(dkv_full); ++kt_cnt; }
       };
       for (int it = 0; it < my_items; ++it) {
@@ -589,9 +599,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t pair_cnt = 0, kt_cnt = 0;
     // kernel parameters copied to registers once (see SoftmaxCtx)
-    const int pH = p.H, pNq = p.Nq, pNk = p.Nk, pQT = p.QT, pKT = p.KT;
-    const float p_scale = p.scale, p_scale_log2 = p.scale_log2;
-    const float* __restrict__ p_lse = p.lse;
+    const int pH = pin_reg(p.H), pNq = pin_reg(p.Nq), pNk = pin_reg(p.Nk), pQT = pin_reg(p.QT),
+              pKT = pin_reg(p.KT);
+    const float p_scale = pin_reg(p.scale), p_scale_log2 = pin_reg(p.scale_log2);
+    const float* __restrict__ p_lse = pin_reg(p.lse);
     for (int it = 0; it < my_items; ++it) {
       const int bh = blockIdx.x + it * gridDim.x;
       const int h = bh % pH, b = bh / pH;
@@ -599,6 +610,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // ---- prologue: delta = rowsum(O o dO), lse in log2 units
       mbar_wait(o_in_full, ph);
       mbar_wait(in_full, ph);
+      if (tid == 0) BWD_DBG(7, pair_cnt);
       {
         const int r = tid;                   // 256 threads, 256 rows
         const uint32_t rsw = static_cast<uint32_t>(r & 7);
@@ -620,11 +632,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       named_bar_sync(2, 256);
       __syncwarp();
       if (lane == 0) mbar_arrive(stat_ready);
+      if (tid == 0) BWD_DBG(8, pair_cnt);
 
       for (int kt = 0; kt < pKT; ++kt) {
         for (int qt = 0; qt < pQT; ++qt, ++pair_cnt) {
           const uint32_t pp = pair_cnt & 1u;
           mbar_wait(sdp_full, pp);
+          if (tid == 0) BWD_DBG(0, pair_cnt);
           tc_fence_after();
           const int qrow = qt * TQ + row;
           const bool row_ok = qrow < pNq;
@@ -645,7 +659,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               pe[j] = ok ? ((j & 2) ? ex2_poly(xa) : ex2_mufu(xa)) : 0.f;
             }
           }
+          if (tid == 0) BWD_DBG(1, pair_cnt);
           mbar_wait(pds_empty, pp ^ 1u);
+          if (tid == 0) BWD_DBG(2, pair_cnt);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t dv[32];
@@ -676,10 +692,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_full);
+          if (tid == 0) BWD_DBG(4, pair_cnt);
 
           if (qt == pQT - 1) {
             // ---- dV_kt, dK_kt complete: TMEM -> bf16 -> staging -> TMA store (rows = keys)
+            if (tid == 0) BWD_DBG(9, pair_cnt);
             mbar_wait(dkv_full, kt_cnt & 1u);
+            if (tid == 0) BWD_DBG(10, pair_cnt);
             tc_fence_after();
             uint32_t a[32], c[32];
             tmem_ld_32x32b_x32(tmem_base + lane_addr + DV_COL + hf * 32, a);
@@ -714,7 +733,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       // ---- dQ tiles complete
+      if (tid == 0) BWD_DBG(11, pair_cnt - 1);
       mbar_wait(dq_full, ph);
+      if (tid == 0) BWD_DBG(12, pair_cnt - 1);
       tc_fence_after();
       for (int qt = 0; qt < pQT; ++qt) {
         uint32_t a[32];
@@ -838,6 +859,7 @@ int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
   p.scale = a.scale;
   p.scale_log2 = a.scale * LOG2E;
   p.lse = a.lse;
+  p.dbg = attn_debug_buffer();
   const int cols = a.H * DH;
   CUtensorMap tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV;
   if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, BWD_ROWS))) return rc;

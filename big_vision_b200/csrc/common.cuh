@@ -23,6 +23,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// Pins a value in a register: kernel parameters live in the constant bank, and ptxas prefers to
+// RE-LOAD them (LDC / LDCU, ~40 cycles on the dependency chain) at every use inside unrolled
+// loops instead of keeping a hoisted copy -- an empty inline asm does not stop it (nothing reaches
+// ptxas).  Routing the value through a warp shuffle from the thread's own lane does: the result
+// is opaque, costs one SHFL per kernel, and must be called with the full warp converged.
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
+  return __shfl_sync(0xffffffffu, v, static_cast<int>(threadIdx.x & 31));
+}
+__device__ __forceinline__ int pin_reg(int v) { return static_cast<int>(pin_reg(static_cast<uint32_t>(v))); }
+__device__ __forceinline__ float pin_reg(float v) { return __uint_as_float(pin_reg(__float_as_uint(v))); }
+template <typename T>
+__device__ __forceinline__ T* pin_reg(T* v) {
+  const unsigned long long u = reinterpret_cast<unsigned long long>(v);
+  const uint32_t lo = pin_reg(static_cast<uint32_t>(u)), hi = pin_reg(static_cast<uint32_t>(u >> 32));
+  return reinterpret_cast<T*>((static_cast<unsigned long long>(hi) << 32) | lo);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -267,10 +267,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_after();
           const uint32_t a_s = base + stage * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_STAGE_BYTES;
+          const uint64_t adesc0 = umma_smem_desc_sw128(a_s, a_lbo, 1024u);
+          const uint64_t bdesc0 = umma_smem_desc_sw128(b_s, b_lbo, 1024u);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = umma_smem_desc_sw128(a_s + k * a_kstep, a_lbo, 1024u);
-            const uint64_t bdesc = umma_smem_desc_sw128(b_s + k * b_kstep, b_lbo, 1024u);
+            // stepping along K only bumps the 16-byte-granular start-address field
+            const uint64_t adesc = adesc0 + k * (a_kstep >> 4);
+            const uint64_t bdesc = bdesc0 + k * (b_kstep >> 4);
             const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
             if (CTAS == 2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, accf);
             else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accf);
@@ -300,10 +303,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t flush = 0;
     // kernel parameters used per element are copied to registers once (constant-bank reads inside
     // the unrolled column loop would put an LDCU round trip on every group's dependency chain)
-    const int pM = p.M, pN = p.N, p_mod = p.aux_row_mod, p_reduce = p.reduce_out;
-    const float p_alpha = p.alpha;
-    const float* __restrict__ p_bias = p.bias;
-    const bf16* __restrict__ p_aux = p.aux;
+    const int pM = pin_reg(p.M), pN = pin_reg(p.N), p_mod = pin_reg(p.aux_row_mod),
+              p_reduce = pin_reg(p.reduce_out);
+    const float p_alpha = pin_reg(p.alpha);
+    const float* __restrict__ p_bias = pin_reg(p.bias);
+    const bf16* __restrict__ p_aux = pin_reg(p.aux);
     const long long p_ldaux = p.ldaux;
     const bool unit_alpha = (p_alpha == 1.0f);
     constexpr bool HAS_AUX = (EF == EF_RESID || EF == EF_DGELU);
