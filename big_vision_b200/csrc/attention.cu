@@ -430,7 +430,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   P  = exp(scale S - lse)    dS = scale * P o (dP - delta)      (registers -> smem bf16)
 //   dV_kt += P^T dO_qt         dK_kt += dS^T Q_qt      dQ_qt += dS K_kt     (TMEM)
 // delta_i = sum_j O_ij dO_ij is computed in the prologue from the O tile.
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = 512;   // WG0,1 compute; WG2: warp 8 TMA, 9 MMA; WG3: gradient write-out
 constexpr int BWD_ROWS = 256;                       // smem rows per operand (zero-filled past N)
 constexpr int OP_BYTES = BWD_ROWS * 128;            // 32 KB
 struct BwdDev {
@@ -481,8 +481,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(o_in_full, 1); mbar_init(stat_ready, 8);
     mbar_init(sdp_full, 1);  mbar_init(sdp_empty, 8);
     mbar_init(pds_full, 8);  mbar_init(pds_empty, 1);
-    mbar_init(dkv_full, 1);  mbar_init(dkv_empty, 8);
-    mbar_init(dq_full, 1);   mbar_init(dq_empty, 8);
+    mbar_init(dkv_full, 1);  mbar_init(dkv_empty, 4);   // *_empty: one arrive per write-out warp
+    mbar_init(dq_full, 1);   mbar_init(dq_empty, 4);
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -495,6 +495,66 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int my_items = (p.BH - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                        static_cast<int>(gridDim.x);
 
+  if (warp >= 12) {
+    // ---------------- gradient write-out warpgroup ----------------
+    // dV/dK (once per key tile) and dQ (once per item): TMEM -> bf16 -> swizzled staging -> TMA
+    // store, concurrently with the compute warps working on the next (key, query) tile pair.
+    reg_dec<112>();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int etid = threadIdx.x - 384;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int pH = pin_reg(p.H), pQT = pin_reg(p.QT), pKT = pin_reg(p.KT);
+    uint32_t kt_cnt = 0;
+    auto write_tile = [&](uint32_t tcol, const CUtensorMap* tm, int h, int r0, int b) {
+      uint32_t a[64];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + tcol, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
+      tmem_ld_wait();
+      if (etid == 0) tma_store_wait_read<0>();
+      named_bar_sync(3, 128);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t addr = stg_s + row * 128 + ((static_cast<uint32_t>(g) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                     "r"(pack_bf16(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]))),
+                     "r"(pack_bf16(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]))),
+                     "r"(pack_bf16(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]))),
+                     "r"(pack_bf16(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]))) : "memory");
+      }
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (etid == 0) {
+        tma_store_3d(tm, stg_s, h * DH, r0, b);
+        tma_store_commit();
+      }
+    };
+    for (int it = 0; it < my_items; ++it) {
+      const int bh = blockIdx.x + it * gridDim.x;
+      const int h = bh % pH, b = bh / pH;
+      const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+      for (int kt = 0; kt < pKT; ++kt, ++kt_cnt) {
+        mbar_wait(dkv_full, kt_cnt & 1u);
+        tc_fence_after();
+        write_tile(DV_COL, &tmdV, h, kt * TQ, b);
+        write_tile(DK_COL, &tmdK, h, kt * TQ, b);
+        // both accumulators are in registers / staged: the MMA warp may start the next key tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_empty);
+      }
+      mbar_wait(dq_full, ph);
+      tc_fence_after();
+      for (int qt = 0; qt < pQT; ++qt) write_tile(DQ_COL + qt * DH, &tmdQ, h, qt * TQ, b);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+    }
+    if (etid == 0) tma_store_wait<0>();
+  } else if (warp >= 8) {
+    reg_dec<40>();
+  }
   if (warp == 8) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
@@ -590,14 +650,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(in_empty);
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ---------------- compute warps ----------------
+    reg_inc<176>();
     const int quarter = warp & 3, hf = warp >> 2;
     const int row = quarter * 32 + lane;
     const int tid = threadIdx.x;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t pair_cnt = 0, kt_cnt = 0;
+    uint32_t pair_cnt = 0;
     // kernel parameters copied to registers once (see SoftmaxCtx)
     const int pH = pin_reg(p.H), pNq = pin_reg(p.Nq), pNk = pin_reg(p.Nk), pQT = pin_reg(p.QT),
               pKT = pin_reg(p.KT);
@@ -651,12 +712,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
-              const int kcol = kt * TQ + hf * 64 + j;
-              const bool ok = row_ok && (kcol < pNk);
+              // No masking is needed here: padded query rows have lse = +inf (so P ~ 0), zero dO and
+              // zero Q rows; padded key columns only feed dV/dK rows that the TMA store clips and a
+              // dQ product against zero-filled K rows.  Everything stays finite.
+              // Exponentials alternate between MUFU and the FMA-pipe polynomial (see ex2_poly).
               const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
-              // exponentials alternate between MUFU and the FMA-pipe polynomial (see ex2_poly)
-              const float xa = sj * p_scale_log2 - l2;
-              pe[j] = ok ? ((j & 2) ? ex2_poly(xa) : ex2_mufu(xa)) : 0.f;
+              const float xa = fmaf(sj, p_scale_log2, -l2);
+              pe[j] = (j & 2) ? ex2_poly(xa) : ex2_mufu(xa);
             }
           }
           if (tid == 0) BWD_DBG(1, pair_cnt);
@@ -682,7 +744,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const float d0 = p_scale * pe[j] * (__uint_as_float(dv[(j & 31)]) - dl);
                 const float d1 = p_scale * pe[j + 1] * (__uint_as_float(dv[(j & 31) + 1]) - dl);
                 pk[j2] = pack_bf16(pe[j], pe[j + 1]);
-                dk[j2] = pack_bf16(pe[j] != 0.f ? d0 : 0.f, pe[j + 1] != 0.f ? d1 : 0.f);
+                dk[j2] = pack_bf16(d0, d1);
               }
               const uint32_t off = hf * TILE_BYTES + row * 128 + ((static_cast<uint32_t>(u) ^ sw) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_s + off), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
@@ -694,79 +756,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (lane == 0) mbar_arrive(pds_full);
           if (tid == 0) BWD_DBG(4, pair_cnt);
 
-          if (qt == pQT - 1) {
-            // ---- dV_kt, dK_kt complete: TMEM -> bf16 -> staging -> TMA store (rows = keys)
-            if (tid == 0) BWD_DBG(9, pair_cnt);
-            mbar_wait(dkv_full, kt_cnt & 1u);
-            if (tid == 0) BWD_DBG(10, pair_cnt);
-            tc_fence_after();
-            uint32_t a[32], c[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + DV_COL + hf * 32, a);
-            tmem_ld_32x32b_x32(tmem_base + lane_addr + DK_COL + hf * 32, c);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dkv_empty);
-            ++kt_cnt;
-            for (int which = 0; which < 2; ++which) {
-              if (tid == 0) tma_store_wait_read<0>();
-              named_bar_sync(2, 256);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
-                const uint32_t addr = stg_s + row * 128 + ((piece ^ sw) << 4);
-                const uint32_t* src = which == 0 ? a : c;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 0]), __uint_as_float(src[g * 8 + 1]))),
-                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 2]), __uint_as_float(src[g * 8 + 3]))),
-                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 4]), __uint_as_float(src[g * 8 + 5]))),
-                             "r"(pack_bf16(__uint_as_float(src[g * 8 + 6]), __uint_as_float(src[g * 8 + 7]))) : "memory");
-              }
-              fence_proxy_async();
-              named_bar_sync(2, 256);
-              if (tid == 0) {
-                tma_store_3d(which == 0 ? &tmdV : &tmdK, stg_s, h * DH, kt * TQ, b);
-                tma_store_commit();
-              }
-            }
-          }
-        }
-      }
-      // ---- dQ tiles complete
-      if (tid == 0) BWD_DBG(11, pair_cnt - 1);
-      mbar_wait(dq_full, ph);
-      if (tid == 0) BWD_DBG(12, pair_cnt - 1);
-      tc_fence_after();
-      for (int qt = 0; qt < pQT; ++qt) {
-        uint32_t a[32];
-        tmem_ld_32x32b_x32(tmem_base + lane_addr + DQ_COL + qt * DH + hf * 32, a);
-        tmem_ld_wait();
-        if (qt == pQT - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dq_empty);
-        }
-        if (tid == 0) tma_store_wait_read<0>();
-        named_bar_sync(2, 256);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t piece = static_cast<uint32_t>(hf * 4 + g);
-          const uint32_t addr = stg_s + row * 128 + ((piece ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]))),
-                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]))),
-                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]))),
-                       "r"(pack_bf16(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]))) : "memory");
-        }
-        fence_proxy_async();
-        named_bar_sync(2, 256);
-        if (tid == 0) {
-          tma_store_3d(&tmdQ, stg_s, h * DH, qt * TQ, b);
-          tma_store_commit();
         }
       }
     }
-    if (tid == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
