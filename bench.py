@@ -251,6 +251,27 @@ def run_ours(args):
   barrier()
   ms_e2e = e0.elapsed_time(e1)
 
+  if args.profile_calls and rank == 0:
+    import collections
+    L.PROFILE = []
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    pe0.record()
+    state, m = update_fn(state, None, batch)
+    pe1.record()
+    torch.cuda.synchronize()
+    prof, L.PROFILE = L.PROFILE, None
+    tot, cnt = collections.defaultdict(float), collections.Counter()
+    for name, a, b in prof:
+      tot[name] += a.elapsed_time(b)
+      cnt[name] += 1
+    step_ms = pe0.elapsed_time(pe1)
+    ssum = sum(tot.values())
+    print(f"[profile-calls] step {step_ms:.2f} ms, sum of kernel spans {ssum:.2f} ms, "
+          f"gap {step_ms - ssum:.2f} ms", file=sys.stderr)
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+      print(f"[profile-calls]   {k:24s} {v:8.2f} ms  n={cnt[k]}", file=sys.stderr)
+
   t = torch.tensor([ms, ms_e2e, gemm_ms], dtype=torch.float64, device="cuda")
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,6 +329,8 @@ def main():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--per-gpu-batch", type=int, default=1024)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--profile-calls", action="store_true",
+                  help="time every C-ABI call of one extra step with CUDA events; breakdown on stderr")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)

@@ -558,6 +558,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 8) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
+      // Operands are single-buffered (shared memory is full), so every CTA alternates between an
+      // HBM-bound load phase and a compute phase.  Left alone, all 148 CTAs fall into the same
+      // phase and the loads of one burst share the HBM bandwidth.  Starting the odd CTAs half an
+      // item late puts the two halves of the chip in anti-phase: one half loads while the other
+      // computes.
+      if ((blockIdx.x & 1) && my_items > 1) {
+        const long long t_start = clock64();
+        while (clock64() - t_start < 13000) { }
+      }
       for (int it = 0; it < my_items; ++it) {
         const int bh = blockIdx.x + it * gridDim.x;
         const int h = bh % p.H, b = bh / p.H;
@@ -595,12 +604,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // start-address field (this thread issues 32 MMAs per pair -- its instruction count matters)
         const uint64_t dq_k = umma_smem_desc_sw128(qa, 16, 1024), dk_k = umma_smem_desc_sw128(ka, 16, 1024);
         const uint64_t ddo_k = umma_smem_desc_sw128(da, 16, 1024), dv_k = umma_smem_desc_sw128(va, 16, 1024);
+        // S and dP are independent accumulators: interleaving their K steps keeps two dependent
+        // chains in flight (an MMA that accumulates into the tile of the previous one waits for it)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k) {
           umma_bf16_ss(tmem_base + S_COL, dq_k + k * 2, dk_k + k * 2, id_kk, k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_base + DP_COL, ddo_k + k * 2, dv_k + k * 2, id_kk, k > 0 ? 1u : 0u);
+        }
         umma_commit(sdp_full);
         BWD_DBG(5, sdp_cnt - 1);
       };
@@ -620,14 +630,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t ddo_mn = umma_smem_desc_sw128(da, 8192, 1024);
         const uint64_t dq_mn = umma_smem_desc_sw128(qa, 8192, 1024);
         const uint64_t dk_mn = umma_smem_desc_sw128(ka, 8192, 1024);
+        // three independent accumulation chains (dV, dK, dQ) issued round-robin
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {   // contraction over 128 query rows, 16 per step (2048 B)
+        for (int jj = 0; jj < 8; ++jj) {
           const uint32_t accv = (qt > 0 || jj > 0) ? 1u : 0u;
+          // dV, dK: contraction over the 128 query rows, 16 per step (2048 B in the MN-major tiles)
           umma_bf16_ss(tmem_base + DV_COL, dp_mn + jj * 128, ddo_mn + jj * 128, id_mm, accv);
           umma_bf16_ss(tmem_base + DK_COL, dds_mn + jj * 128, dq_mn + jj * 128, id_mm, accv);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {   // contraction over 128 keys
+          // dQ: contraction over the 128 keys
           umma_bf16_ss(tmem_base + DQ_COL + qt * DH, dds_k + (jj >> 2) * (TILE_BYTES / 16) + (jj & 3) * 2,
                        dk_mn + jj * 128, id_km, (kt > 0 || jj > 0) ? 1u : 0u);
         }

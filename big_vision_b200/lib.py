@@ -121,7 +121,19 @@ LAUNCHES = [0]
 _LAUNCHES_PER_CALL = {"bv_embed_bwd": 2}
 
 
+# optional in-situ timing of every C-ABI call (bench.py --profile-calls): list of (name, e0, e1)
+PROFILE = None
+
+
 def call(name, *args):
   lib = load()
-  check(getattr(lib, name)(*args), name)
+  if PROFILE is not None:
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(getattr(lib, name)(*args), name)
+    e1.record()
+    PROFILE.append((name, e0, e1))
+  else:
+    check(getattr(lib, name)(*args), name)
   LAUNCHES[0] += _LAUNCHES_PER_CALL.get(name, 1)
