@@ -25,6 +25,7 @@ int bv_gemm(const bv_gemm_args* a, void* stream) {
   if (!a) { set_error("bv_gemm: null args"); return BV_ERR_INVALID; }
   GemmArgs g;
   g.A = a->A; g.B = a->B; g.D = a->D; g.D2 = a->D2; g.bias = a->bias; g.aux = a->aux;
+  g.colsum = a->colsum;
   g.M = a->M; g.N = a->N; g.K = a->K;
   g.lda = a->lda; g.ldb = a->ldb; g.ldd = a->ldd; g.ldd2 = a->ldd2; g.ldaux = a->ldaux;
   g.a_mn = a->a_mn; g.b_mn = a->b_mn; g.epi = a->epilogue; g.out_dtype = a->out_dtype;
@@ -67,6 +68,7 @@ int bv_attention_bwd(const bv_attn_bwd_args* a, void* stream) {
   g.dq = a->dq; g.dk = a->dk; g.dv = a->dv;
   g.lddq = a->lddq; g.lddk = a->lddk; g.lddv = a->lddv;
   g.bsdq = a->bsdq; g.bsdk = a->bsdk; g.bsdv = a->bsdv;
+  g.dq_colsum = a->dq_colsum; g.dk_colsum = a->dk_colsum; g.dv_colsum = a->dv_colsum;
   g.delta = nullptr;
   return launch_attention_bwd(g, S(stream));
 }

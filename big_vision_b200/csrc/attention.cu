@@ -437,6 +437,10 @@ struct BwdDev {
   int BH, H, Nq, Nk, QT, KT;
   float scale, scale_log2;
   const float* lse;
+  const bf16* o;     // forward output and its gradient, read straight from global memory for
+  const bf16* d_o;   // delta = rowsum(O o dO) (element (b,t,h*64+j) at b*bs + t*ld + h*64 + j)
+  long long ldo, bso, lddo, bsdo;
+  float* dq_colsum; float* dk_colsum; float* dv_colsum;   // optional [H*64] bias gradients
   long long* dbg;    // optional timeline of CTA 0 (BV_ATTN_DBG=1)
 };
 // dbg[256 + slot] : per-pair events (16 per pair, first 12 pairs) of CTA 0
@@ -449,7 +453,7 @@ constexpr int BWD_P_OFF = 4 * OP_BYTES;                       // P  [128 x 128] 
 constexpr int BWD_DS_OFF = BWD_P_OFF + 2 * TILE_BYTES;        // dS [128 x 128]
 constexpr int BWD_STG_OFF = BWD_DS_OFF + 2 * TILE_BYTES;      // 16 KB output staging
 constexpr int BWD_STAT_OFF = BWD_STG_OFF + TILE_BYTES;        // lse2[256], delta[256]
-constexpr int BWD_BAR_OFF = BWD_STAT_OFF + 2 * BWD_ROWS * 4;
+constexpr int BWD_BAR_OFF = BWD_STAT_OFF + 4 * BWD_ROWS * 4;   // lse2 / delta, double-buffered per item
 constexpr int BWD_SMEM = BWD_BAR_OFF + 128 + 1024;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -465,7 +469,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t q_s = base, k_s = base + OP_BYTES, v_s = base + 2 * OP_BYTES, do_s = base + 3 * OP_BYTES;
   const uint32_t p_s = base + BWD_P_OFF, ds_s = base + BWD_DS_OFF, stg_s = base + BWD_STG_OFF;
   float* lse2_s = reinterpret_cast<float*>(base_ptr + BWD_STAT_OFF);
-  float* delta_s = lse2_s + BWD_ROWS;
+  float* delta_s = lse2_s + 2 * BWD_ROWS;
   const uint32_t bar = base + BWD_BAR_OFF;
   const uint32_t in_full = bar, in_empty = bar + 8, o_in_full = bar + 16, stat_ready = bar + 24;
   const uint32_t sdp_full = bar + 32, sdp_empty = bar + 40, pds_full = bar + 48, pds_empty = bar + 56;
@@ -507,7 +511,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int pH = pin_reg(p.H), pQT = pin_reg(p.QT), pKT = pin_reg(p.KT);
     uint32_t kt_cnt = 0;
-    auto write_tile = [&](uint32_t tcol, const CUtensorMap* tm, int h, int r0, int b) {
+    const int pNq = pin_reg(p.Nq), pNk = pin_reg(p.Nk);
+    auto write_tile = [&](uint32_t tcol, const CUtensorMap* tm, int h, int r0, int b, float* colsum, int nvalid) {
       uint32_t a[64];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + tcol, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
       tmem_ld_32x32b_x32(tmem_base + lane_addr + tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
@@ -525,6 +530,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async();
       named_bar_sync(3, 128);
+      if (colsum != nullptr) {
+        // bias gradient of the projection that produced q/k/v: column sums of the staged tile over
+        // its valid rows (thread t: column t % 64, half of the rows)
+        const int cc = etid & 63, r_lo = (etid >> 6) * 64;
+        const uint32_t cbase = stg_s + static_cast<uint32_t>(cc & 7) * 2;
+        float csum = 0.f;
+        for (int r = r_lo; r < r_lo + 64 && r0 + r < nvalid; ++r) {
+          uint16_t hv;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv)
+                       : "r"(cbase + r * 128 + ((static_cast<uint32_t>(cc >> 3) ^ static_cast<uint32_t>(r & 7)) << 4)));
+          csum += __uint_as_float(static_cast<uint32_t>(hv) << 16);
+        }
+        atomicAdd(colsum + h * DH + cc, csum);
+      }
       if (etid == 0) {
         tma_store_3d(tm, stg_s, h * DH, r0, b);
         tma_store_commit();
@@ -537,8 +556,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int kt = 0; kt < pKT; ++kt, ++kt_cnt) {
         mbar_wait(dkv_full, kt_cnt & 1u);
         tc_fence_after();
-        write_tile(DV_COL, &tmdV, h, kt * TQ, b);
-        write_tile(DK_COL, &tmdK, h, kt * TQ, b);
+        write_tile(DV_COL, &tmdV, h, kt * TQ, b, p.dv_colsum, pNk);
+        write_tile(DK_COL, &tmdK, h, kt * TQ, b, p.dk_colsum, pNk);
         // both accumulators are in registers / staged: the MMA warp may start the next key tile
         tc_fence_before();
         __syncwarp();
@@ -546,7 +565,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       mbar_wait(dq_full, ph);
       tc_fence_after();
-      for (int qt = 0; qt < pQT; ++qt) write_tile(DQ_COL + qt * DH, &tmdQ, h, qt * TQ, b);
+      for (int qt = 0; qt < pQT; ++qt) write_tile(DQ_COL + qt * DH, &tmdQ, h, qt * TQ, b, p.dq_colsum, pNq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);
@@ -573,9 +592,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ph = static_cast<uint32_t>(it) & 1u;
         // operands are free once every MMA of the previous item retired
         mbar_wait(in_empty, ph ^ 1u);
-        // O goes into the P buffer, which the previous item's MMAs have also released
-        mbar_expect_tx(o_in_full, OP_BYTES);
-        tma_load_3d(p_s, &tmO, o_in_full, h * DH, 0, b);
         mbar_expect_tx(in_full, 4 * OP_BYTES);
         tma_load_3d(do_s, &tmdO, in_full, h * DH, 0, b);
         tma_load_3d(q_s, &tmQ, in_full, h * DH, 0, b);
@@ -648,7 +664,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int it = 0; it < my_items; ++it) {
         const uint32_t ph = static_cast<uint32_t>(it) & 1u;
         mbar_wait(in_full, ph);
-        mbar_wait(stat_ready, ph);   // the compute warps are done with O in the P buffer
         // software pipeline: S/dP of pair j+1 are issued BEFORE the gradient products of pair j,
         // so the compute warps can start on pair j+1 while the tensor core finishes pair j
         issue_sdp(0);
@@ -674,36 +689,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               pKT = pin_reg(p.KT);
     const float p_scale = pin_reg(p.scale), p_scale_log2 = pin_reg(p.scale_log2);
     const float* __restrict__ p_lse = pin_reg(p.lse);
+    const bf16* __restrict__ p_o = pin_reg(p.o);
+    const bf16* __restrict__ p_do = pin_reg(p.d_o);
+    const long long p_ldo = p.ldo, p_bso = p.bso, p_lddo = p.lddo, p_bsdo = p.bsdo;
     for (int it = 0; it < my_items; ++it) {
       const int bh = blockIdx.x + it * gridDim.x;
       const int h = bh % pH, b = bh / pH;
       const uint32_t ph = static_cast<uint32_t>(it) & 1u;
-      // ---- prologue: delta = rowsum(O o dO), lse in log2 units
-      mbar_wait(o_in_full, ph);
-      mbar_wait(in_full, ph);
-      if (tid == 0) BWD_DBG(7, pair_cnt);
+      // ---- prologue: delta = rowsum(O o dO) and lse (log2 units) for the 256 row slots of this
+      // item, straight from global memory (one row per thread) while the TMA loads are in flight
+      float* lse2_i = lse2_s + (it & 1) * BWD_ROWS;
+      float* delta_i = delta_s + (it & 1) * BWD_ROWS;
       {
-        const int r = tid;                   // 256 threads, 256 rows
-        const uint32_t rsw = static_cast<uint32_t>(r & 7);
-        float acc = 0.f;
+        const int r = tid;
+        float acc = 0.f, l2v = INFINITY;
+        if (r < pNq) {
+          const uint4* po = reinterpret_cast<const uint4*>(p_o + b * p_bso + r * p_ldo + h * DH);
+          const uint4* pd = reinterpret_cast<const uint4*>(p_do + b * p_bsdo + r * p_lddo + h * DH);
+          uint4 ao[8], ad[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t off = (r >> 7) * TILE_BYTES + (r & 127) * 128 + ((static_cast<uint32_t>(c) ^ rsw) << 4);
-          uint4 a, d;
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(p_s + off));
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "r"(do_s + off));
-          acc += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x);
-          acc += bf16_lo(a.y) * bf16_lo(d.y) + bf16_hi(a.y) * bf16_hi(d.y);
-          acc += bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z);
-          acc += bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+          for (int c = 0; c < 8; ++c) { ao[c] = __ldg(po + c); ad[c] = __ldg(pd + c); }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            acc += bf16_lo(ao[c].x) * bf16_lo(ad[c].x) + bf16_hi(ao[c].x) * bf16_hi(ad[c].x);
+            acc += bf16_lo(ao[c].y) * bf16_lo(ad[c].y) + bf16_hi(ao[c].y) * bf16_hi(ad[c].y);
+            acc += bf16_lo(ao[c].z) * bf16_lo(ad[c].z) + bf16_hi(ao[c].z) * bf16_hi(ad[c].z);
+            acc += bf16_lo(ao[c].w) * bf16_lo(ad[c].w) + bf16_hi(ao[c].w) * bf16_hi(ad[c].w);
+          }
+          l2v = p_lse[static_cast<int64_t>(bh) * pNq + r] * LOG2E;
         }
-        delta_s[r] = acc;
-        lse2_s[r] = (r < pNq) ? p_lse[static_cast<int64_t>(bh) * pNq + r] * LOG2E : INFINITY;
+        delta_i[r] = acc;
+        lse2_i[r] = l2v;
       }
       named_bar_sync(2, 256);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(stat_ready);
-      if (tid == 0) BWD_DBG(8, pair_cnt);
+      mbar_wait(in_full, ph);
+      if (tid == 0) BWD_DBG(7, pair_cnt);
 
       for (int kt = 0; kt < pKT; ++kt) {
         for (int qt = 0; qt < pQT; ++qt, ++pair_cnt) {
@@ -713,7 +733,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_after();
           const int qrow = qt * TQ + row;
           const bool row_ok = qrow < pNq;
-          const float l2 = lse2_s[qrow], dl = delta_s[qrow];
+          const float l2 = lse2_i[qrow], dl = delta_i[qrow];
           float pe[64];
           {
             uint32_t t0[32], t1[32];
@@ -861,6 +881,15 @@ int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
   p.scale = a.scale;
   p.scale_log2 = a.scale * LOG2E;
   p.lse = a.lse;
+  p.o = reinterpret_cast<const bf16*>(a.o);
+  p.d_o = reinterpret_cast<const bf16*>(g.d_o);
+  p.ldo = a.ldo; p.bso = a.bso; p.lddo = g.lddo; p.bsdo = g.bsdo;
+  p.dq_colsum = g.dq_colsum; p.dk_colsum = g.dk_colsum; p.dv_colsum = g.dv_colsum;
+  if ((reinterpret_cast<uintptr_t>(a.o) & 15) || (reinterpret_cast<uintptr_t>(g.d_o) & 15) ||
+      (a.ldo % 8) || (g.lddo % 8) || (a.bso % 8) || (g.bsdo % 8)) {
+    set_error("bv_attention_bwd: o / d_o must be 16B aligned with strides that are multiples of 8");
+    return BV_ERR_INVALID;
+  }
   p.dbg = attn_debug_buffer();
   const int cols = a.H * DH;
   CUtensorMap tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV;

@@ -75,6 +75,7 @@ struct GemmDev {
   float alpha;
   const float* bias;
   const bf16* aux;
+  float* colsum;         // optional bias-gradient accumulator (bf16 outputs only)
   long long ldaux;
   int aux_row_mod;
 };
@@ -308,6 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const float p_alpha = pin_reg(p.alpha);
     const float* __restrict__ p_bias = pin_reg(p.bias);
     const bf16* __restrict__ p_aux = pin_reg(p.aux);
+    float* __restrict__ p_colsum = pin_reg(p.colsum);
     const long long p_ldaux = p.ldaux;
     const bool unit_alpha = (p_alpha == 1.0f);
     constexpr bool HAS_AUX = (EF == EF_RESID || EF == EF_DGELU);
@@ -455,6 +457,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         fence_proxy_async();
         named_bar_sync(1, EPI_THREADS);
+        if (!OUT_F32 && p_colsum != nullptr && ep_tid < 128) {
+          // bias gradient fused into the producer: column sums of the staged (bf16-rounded) tile.
+          // Thread t owns column t % 64 over half of the 128 rows; rows past M hold exact zeros.
+          const int cc = ep_tid & 63, r_lo = (ep_tid >> 6) * 64;
+          const uint32_t cbase = buf + static_cast<uint32_t>(cc & 7) * 2;
+          float csum = 0.f;
+#pragma unroll 8
+          for (int r = r_lo; r < r_lo + 64; ++r) {
+            uint16_t hv;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv)
+                         : "r"(cbase + r * 128 + ((static_cast<uint32_t>(cc >> 3) ^ static_cast<uint32_t>(r & 7)) << 4)));
+            csum += __uint_as_float(static_cast<uint32_t>(hv) << 16);
+          }
+          const int ncol = n0 + c * CH + cc;
+          if (ncol < pN) atomicAdd(p_colsum + ncol, csum);
+        }
         if (ep_tid == 0) {
           const int c0 = n0 + c * CH;
           if (c0 < pN) {
@@ -539,6 +557,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   p.a_mn = g.a_mn; p.b_mn = g.b_mn; p.reduce_out = g.reduce_out;
   p.alpha = g.alpha;
   p.bias = g.bias;
+  p.colsum = g.colsum;
   p.aux = reinterpret_cast<const bf16*>(g.aux);
   p.ldaux = g.ldaux;
   p.aux_row_mod = g.aux_row_mod;
@@ -614,6 +633,9 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     set_error("bv_gemm: BIAS_GELU needs bf16 output, D2 and no reduce"); return BV_ERR_INVALID;
   }
   if (g.out_dtype != DT_F32 && g.out_dtype != DT_BF16) { set_error("bv_gemm: bad out dtype"); return BV_ERR_INVALID; }
+  if (g.colsum != nullptr && (g.out_dtype != DT_BF16 || g.reduce_out)) {
+    set_error("bv_gemm: colsum needs a plain bf16 output"); return BV_ERR_INVALID;
+  }
   int bn = g.block_n;
   if (bn == 0) bn = (g.N > 128) ? 256 : 128;
   // BV_GEMM_CTAS=1 selects the single-CTA (cta_group::1) build of the same kernel: a

@@ -10,6 +10,7 @@ enum : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_RESID = 3, 
 struct GemmArgs {
   const void* A; const void* B; void* D; void* D2;
   const float* bias; const void* aux;
+  float* colsum;                        // optional [N] fp32: += column sums of the stored bf16 output
   int64_t M, N, K;
   int64_t lda, ldb, ldd, ldd2, ldaux;   // element strides of the stored matrices
   int a_mn, b_mn;                       // 0 = K-major storage, 1 = MN-major storage
@@ -42,6 +43,7 @@ struct AttnBwdArgs {
   AttnArgs f;
   const void* d_o; int64_t lddo, bsdo;
   void* dq; void* dk; void* dv;                  // bf16, same geometry as q/k/v
+  float* dq_colsum; float* dk_colsum; float* dv_colsum;   // optional [H*64] fp32 bias gradients
   int64_t lddq, lddk, lddv, bsdq, bsdk, bsdv;
   float* delta;                                  // workspace [B, H, Nq]
 };

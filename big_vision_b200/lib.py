@@ -17,7 +17,7 @@ EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_DGELU = 0, 1, 2, 3, 4
 
 class GemmArgs(ctypes.Structure):
   _fields_ = [("A", c_vp), ("B", c_vp), ("D", c_vp), ("D2", c_vp), ("bias", c_vp), ("aux", c_vp),
-              ("M", c_i64), ("N", c_i64), ("K", c_i64),
+              ("colsum", c_vp), ("M", c_i64), ("N", c_i64), ("K", c_i64),
               ("lda", c_i64), ("ldb", c_i64), ("ldd", c_i64), ("ldd2", c_i64), ("ldaux", c_i64),
               ("a_mn", c_i32), ("b_mn", c_i32),
               ("epilogue", c_i32), ("out_dtype", c_i32), ("reduce_out", c_i32), ("splits", c_i32),
@@ -36,7 +36,8 @@ class AttnBwdArgs(ctypes.Structure):
   _fields_ = [("fwd", AttnArgs), ("d_o", c_vp), ("lddo", c_i64), ("bsdo", c_i64),
               ("dq", c_vp), ("dk", c_vp), ("dv", c_vp),
               ("lddq", c_i64), ("lddk", c_i64), ("lddv", c_i64),
-              ("bsdq", c_i64), ("bsdk", c_i64), ("bsdv", c_i64)]
+              ("bsdq", c_i64), ("bsdk", c_i64), ("bsdv", c_i64),
+              ("dq_colsum", c_vp), ("dk_colsum", c_vp), ("dv_colsum", c_vp)]
 
 
 class AdamArgs(ctypes.Structure):
@@ -125,7 +126,7 @@ _LAUNCHES_PER_CALL = {"bv_embed_bwd": 2}
 PROFILE = None
 
 
-def call(name, *args):
+def call(name, *args, tag=None):
   lib = load()
   if PROFILE is not None:
     import torch
@@ -133,7 +134,7 @@ def call(name, *args):
     e0.record()
     check(getattr(lib, name)(*args), name)
     e1.record()
-    PROFILE.append((name, e0, e1))
+    PROFILE.append((tag[0] if tag else name, e0, e1, tag[1] if tag else 0.0))
   else:
     check(getattr(lib, name)(*args), name)
   LAUNCHES[0] += _LAUNCHES_PER_CALL.get(name, 1)

@@ -87,8 +87,9 @@ def mlp_bwd(P, p, dout, saved, want_bias2_grad=True):
   if want_bias2_grad:
     ops.colsum(dout, P.g(p + "Dense_1/bias"))
   ops.gemm(act, dout, a_mn=True, b_mn=True, out=P.g(p + "Dense_1/kernel"), reduce_out=True)
-  dpre = ops.gemm(dout, P.h(p + "Dense_1/kernel"), aux=pre, epilogue=L.EPI_DGELU)
-  ops.colsum(dpre, P.g(p + "Dense_0/bias"))
+  # the Dense_0 bias gradient (column sums of dpre) is accumulated by the same GEMM's epilogue
+  dpre = ops.gemm(dout, P.h(p + "Dense_1/kernel"), aux=pre, epilogue=L.EPI_DGELU,
+                  colsum=P.g(p + "Dense_0/bias"))
   ops.gemm(y, dpre, a_mn=True, b_mn=True, out=P.g(p + "Dense_0/kernel"), reduce_out=True)
   return ops.gemm(dpre, P.h(p + "Dense_0/kernel"))
 
@@ -169,11 +170,12 @@ class EncoderBlock:
     qkv3 = qkv.view(n, N, 3 * d)
     dqkv = torch.empty_like(qkv)
     dqkv3 = dqkv.view(n, N, 3 * d)
+    gb = P.g(self.att + "qkv/bias")     # q|k|v bias gradients come out of the attention backward
     ops.attention_bwd(do.view(n, N, d), qkv3[:, :, 0:d], qkv3[:, :, d:2 * d], qkv3[:, :, 2 * d:],
                       o, lse, self.heads, dq=dqkv3[:, :, 0:d], dk=dqkv3[:, :, d:2 * d],
-                      dv=dqkv3[:, :, 2 * d:])
+                      dv=dqkv3[:, :, 2 * d:], dq_colsum=gb[0:d], dk_colsum=gb[d:2 * d],
+                      dv_colsum=gb[2 * d:])
     del do
-    ops.colsum(dqkv, P.g(self.att + "qkv/bias"))
     ops.gemm(ln1, dqkv, a_mn=True, b_mn=True, out=P.g(self.att + "qkv/kernel"), reduce_out=True)
     dln1 = ops.gemm(dqkv, P.h(self.att + "qkv/kernel"))
     del dqkv

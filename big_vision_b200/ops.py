@@ -40,7 +40,7 @@ def _rowmajor(t):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None,
          aux=None, aux_row_mod=0, epilogue=None, out2=None, reduce_out=False, splits=0,
-         block_n=0, alpha=1.0, M=None, N=None, K=None):
+         block_n=0, alpha=1.0, M=None, N=None, K=None, colsum=None):
   """D[M,N] = epi(alpha * A.B^T) with A,B given as STORED 2-D tensors.
 
   a_mn=False: a is [M,K]; a_mn=True: a is [K,M].  Same for b with N.
@@ -75,6 +75,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
       D2=out2.data_ptr() if out2 is not None else None,
       bias=bias.data_ptr() if bias is not None else None,
       aux=aux.data_ptr() if aux is not None else None,
+      colsum=colsum.data_ptr() if colsum is not None else None,
       M=M, N=N, K=K, lda=lda, ldb=ldb, ldd=ldd, ldd2=ldd2, ldaux=ldaux,
       a_mn=int(a_mn), b_mn=int(b_mn), epilogue=epilogue, out_dtype=_dt(out),
       reduce_out=int(reduce_out), splits=splits, block_n=block_n, aux_row_mod=aux_row_mod,
@@ -82,7 +83,11 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
   for t in (a, b, out):
     if not t.is_cuda:
       raise L.BvError("bv_gemm needs CUDA tensors")
-  L.call("bv_gemm", ctypes.byref(args), _stream())
+  tag = None
+  if L.PROFILE is not None:       # bench.py --profile-calls: one line per GEMM shape
+    tag = (f"bv_gemm {M}x{N}x{K} {'T' if a_mn else 'N'}{'T' if b_mn else 'N'} epi{epilogue}"
+           f"{' f32' if out.dtype == torch.float32 else ''}{' red' if reduce_out else ''}", 2.0 * M * N * K)
+  L.call("bv_gemm", ctypes.byref(args), _stream(), tag=tag)
   if epilogue == L.EPI_BIAS_GELU:
     return out, out2
   return out
@@ -140,7 +145,8 @@ def attention_fwd(q, k, v, heads, scale=None):
   return o, lse
 
 
-def attention_bwd(do, q, k, v, o, lse, heads, scale=None, dq=None, dk=None, dv=None):
+def attention_bwd(do, q, k, v, o, lse, heads, scale=None, dq=None, dk=None, dv=None,
+                  dq_colsum=None, dk_colsum=None, dv_colsum=None):
   if scale is None:
     scale = 1.0 / math.sqrt(64)
   if dq is None:
@@ -155,7 +161,10 @@ def attention_bwd(do, q, k, v, o, lse, heads, scale=None, dq=None, dk=None, dv=N
   dkp, lddk, bsdk = _attn_view(dk)
   dvp, lddv, bsdv = _attn_view(dv)
   args = L.AttnBwdArgs(fwd=f, d_o=dop, lddo=lddo, bsdo=bsdo, dq=dqp, dk=dkp, dv=dvp,
-                       lddq=lddq, lddk=lddk, lddv=lddv, bsdq=bsdq, bsdk=bsdk, bsdv=bsdv)
+                       lddq=lddq, lddk=lddk, lddv=lddv, bsdq=bsdq, bsdk=bsdk, bsdv=bsdv,
+                       dq_colsum=dq_colsum.data_ptr() if dq_colsum is not None else None,
+                       dk_colsum=dk_colsum.data_ptr() if dk_colsum is not None else None,
+                       dv_colsum=dv_colsum.data_ptr() if dv_colsum is not None else None)
   L.call("bv_attention_bwd", ctypes.byref(args), _stream())
   return dq, dk, dv
 

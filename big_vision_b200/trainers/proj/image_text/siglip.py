@@ -33,20 +33,35 @@ class Dist:
     if self.world == 1:
       return x
     out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous())
+    self._timed("nccl_all_gather", lambda: dist.all_gather_into_tensor(out, x.contiguous()))
     return out
 
   def reduce_scatter_rows(self, x):
     if self.world == 1:
       return x
     out = torch.empty((x.shape[0] // self.world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM)
+    self._timed("nccl_reduce_scatter",
+                lambda: dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM))
     return out
 
   def all_reduce_sum(self, x):
     if self.world > 1:
-      dist.all_reduce(x, op=dist.ReduceOp.SUM)
+      self._timed("nccl_all_reduce", lambda: dist.all_reduce(x, op=dist.ReduceOp.SUM))
     return x
+
+  @staticmethod
+  def _timed(name, fn):
+    """Runs a collective; under bench.py --profile-calls it is bracketed by CUDA events like
+    every C-ABI call (NCCL kernels run on the current stream for the default process group)."""
+    from big_vision_b200 import lib as L
+    if L.PROFILE is None:
+      fn()
+      return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    L.PROFILE.append((name, e0, e1, 0.0))
 
 
 def sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal):

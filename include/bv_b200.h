@@ -71,6 +71,7 @@ int bv_device_supported(void);
 typedef struct bv_gemm_args {
   const void* A; const void* B; void* D; void* D2;
   const float* bias; const void* aux;
+  float* colsum;   /* optional fp32 [N]: += column sums of the stored bf16 output (bias gradient) */
   int64_t M, N, K;
   int64_t lda, ldb, ldd, ldd2, ldaux;
   int32_t a_mn, b_mn;
@@ -113,6 +114,9 @@ typedef struct bv_attn_bwd_args {
   const void* d_o; int64_t lddo, bsdo;
   void* dq; void* dk; void* dv;
   int64_t lddq, lddk, lddv, bsdq, bsdk, bsdv;
+  /* optional fp32 [H*64] each: += column sums over the valid rows of dq / dk / dv, i.e. the bias
+   * gradients of the projections that produced q / k / v */
+  float* dq_colsum; float* dk_colsum; float* dv_colsum;
 } bv_attn_bwd_args;
 int bv_attention_bwd(const bv_attn_bwd_args* args, void* stream);
 

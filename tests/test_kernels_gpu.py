@@ -68,8 +68,10 @@ def test_dense_backward_contractions(ops, M, N, K):
   _close(dx, dx_ref, 2 ** -7)
   pr = pre.double().requires_grad_(True)
   O.gelu_tanh(pr).sum().backward()
-  dxg = ops.gemm(dy.cuda(), w.cuda(), aux=pre.cuda(), epilogue=L.EPI_DGELU)
+  db = torch.full((K,), 0.5, device="cuda")             # fused bias gradient: += column sums of dxg
+  dxg = ops.gemm(dy.cuda(), w.cuda(), aux=pre.cuda(), epilogue=L.EPI_DGELU, colsum=db)
   _close(dxg, dx_ref * pr.grad, 2 ** -7)
+  _close(db, 0.5 + dxg.double().sum(0), 1e-5)           # exactly the stored (bf16) values, fp32 sums
   dw = torch.zeros(K, N, device="cuda")
   ops.gemm(x.cuda(), dy.cuda(), a_mn=True, b_mn=True, out=dw, reduce_out=True)
   dw_ref = x.double().T @ dy.double()
@@ -156,6 +158,14 @@ def test_attention_forward_backward(ops, B, H, Nq, Nk):
   _close(dq, qr.grad, 2 ** -5)
   _close(dk, kr.grad, 2 ** -5)
   _close(dv, vr.grad, 2 ** -5)
+  # fused bias gradients of the q/k/v projections: column sums over the valid rows, accumulated
+  cs = torch.ones(3, d, device="cuda")
+  dq2, dk2, dv2 = ops.attention_bwd(do.cuda(), q, k, v, o, lse, H, dq_colsum=cs[0], dk_colsum=cs[1],
+                                    dv_colsum=cs[2])
+  assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
+  for i, t in enumerate((dq, dk, dv)):
+    ref = 1 + t.double().sum((0, 1))
+    assert (cs[i].double() - ref).abs().max().item() <= 1e-4 * (ref.abs().max().item() + 1)
 
 
 def test_attention_rows_are_convex_combinations(ops):
