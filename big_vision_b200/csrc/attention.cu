@@ -533,16 +533,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (colsum != nullptr) {
         // bias gradient of the projection that produced q/k/v: column sums of the staged tile over
         // its valid rows (thread t: column t % 64, half of the rows)
-        const int cc = etid & 63, r_lo = (etid >> 6) * 64;
-        const uint32_t cbase = stg_s + static_cast<uint32_t>(cc & 7) * 2;
-        float csum = 0.f;
-        for (int r = r_lo; r < r_lo + 64 && r0 + r < nvalid; ++r) {
-          uint16_t hv;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv)
-                       : "r"(cbase + r * 128 + ((static_cast<uint32_t>(cc >> 3) ^ static_cast<uint32_t>(r & 7)) << 4)));
-          csum += __uint_as_float(static_cast<uint32_t>(hv) << 16);
+        // warp w sums rows 32w..32w+31, lane l the column pair (2l, 2l+1): every load is one
+        // conflict-free 128-byte row, all 32 loads independent
+        const int r_lo = (etid >> 5) * 32;
+        const uint32_t cp = static_cast<uint32_t>(etid & 31);
+        const uint32_t cbase = stg_s + (cp & 3) * 4;
+        float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int r = r_lo + i;
+          uint32_t w;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w)
+                       : "r"(cbase + r * 128 + (((cp >> 2) ^ static_cast<uint32_t>(r & 7)) << 4)));
+          if (r0 + r >= nvalid) w = 0u;
+          s0[i & 1] += bf16_lo(w);
+          s1[i & 1] += bf16_hi(w);
         }
-        atomicAdd(colsum + h * DH + cc, csum);
+        atomicAdd(colsum + h * DH + 2 * cp, s0[0] + s0[1]);
+        atomicAdd(colsum + h * DH + 2 * cp + 1, s1[0] + s1[1]);
       }
       if (etid == 0) {
         tma_store_3d(tm, stg_s, h * DH, r0, b);
@@ -635,10 +643,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int kt = j / p.QT, qt = j % p.QT;
         const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
         const uint32_t da = do_s + qt * TILE_BYTES;
+        BWD_DBG(10, grad_cnt);
         mbar_wait(pds_full, grad_cnt & 1u);
+        BWD_DBG(8, grad_cnt);
         ++grad_cnt;
         if (qt == 0) mbar_wait(dkv_empty, (kt_cnt & 1u) ^ 1u);
         if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
+        BWD_DBG(9, grad_cnt - 1);
         tc_fence_after();
         const uint64_t dp_mn = umma_smem_desc_sw128(p_s, TILE_BYTES, 1024);
         const uint64_t dds_mn = umma_smem_desc_sw128(ds_s, TILE_BYTES, 1024);
@@ -700,26 +711,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // item, straight from global memory (one row per thread) while the TMA loads are in flight
       float* lse2_i = lse2_s + (it & 1) * BWD_ROWS;
       float* delta_i = delta_s + (it & 1) * BWD_ROWS;
+      // Eight lanes share a row (16 B each), so one warp-wide load touches four full 128-byte
+      // lines: 8x fewer L1 wavefronts than a row per thread.  That matters beyond this loop -- a
+      // congested load pipe also delays the tcgen05.mma issue of the other warps (measured).
       {
-        const int r = tid;
-        float acc = 0.f, l2v = INFINITY;
-        if (r < pNq) {
-          const uint4* po = reinterpret_cast<const uint4*>(p_o + b * p_bso + r * p_ldo + h * DH);
-          const uint4* pd = reinterpret_cast<const uint4*>(p_do + b * p_bsdo + r * p_lddo + h * DH);
-          uint4 ao[8], ad[8];
+        const int chunk = tid & 7;
+        const bf16* po = p_o + b * p_bso + h * DH + chunk * 8;
+        const bf16* pd = p_do + b * p_bsdo + h * DH + chunk * 8;
+        uint4 ao[8], ad[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) { ao[c] = __ldg(po + c); ad[c] = __ldg(pd + c); }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            acc += bf16_lo(ao[c].x) * bf16_lo(ad[c].x) + bf16_hi(ao[c].x) * bf16_hi(ad[c].x);
-            acc += bf16_lo(ao[c].y) * bf16_lo(ad[c].y) + bf16_hi(ao[c].y) * bf16_hi(ad[c].y);
-            acc += bf16_lo(ao[c].z) * bf16_lo(ad[c].z) + bf16_hi(ao[c].z) * bf16_hi(ad[c].z);
-            acc += bf16_lo(ao[c].w) * bf16_lo(ad[c].w) + bf16_hi(ao[c].w) * bf16_hi(ad[c].w);
+        for (int i = 0; i < 8; ++i) {
+          const int r = (tid >> 3) + 32 * i;
+          if (r < pNq) {
+            ao[i] = ld_nc_na(reinterpret_cast<const uint4*>(po + r * p_ldo));
+            ad[i] = ld_nc_na(reinterpret_cast<const uint4*>(pd + r * p_lddo));
+          } else {
+            ao[i] = make_uint4(0u, 0u, 0u, 0u);
+            ad[i] = ao[i];
           }
-          l2v = p_lse[static_cast<int64_t>(bh) * pNq + r] * LOG2E;
         }
-        delta_i[r] = acc;
-        lse2_i[r] = l2v;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float acc = bf16_lo(ao[i].x) * bf16_lo(ad[i].x) + bf16_hi(ao[i].x) * bf16_hi(ad[i].x);
+          acc += bf16_lo(ao[i].y) * bf16_lo(ad[i].y) + bf16_hi(ao[i].y) * bf16_hi(ad[i].y);
+          acc += bf16_lo(ao[i].z) * bf16_lo(ad[i].z) + bf16_hi(ao[i].z) * bf16_hi(ad[i].z);
+          acc += bf16_lo(ao[i].w) * bf16_lo(ad[i].w) + bf16_hi(ao[i].w) * bf16_hi(ad[i].w);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          if (chunk == 0) delta_i[(tid >> 3) + 32 * i] = acc;
+        }
+        lse2_i[tid] = tid < pNq ? p_lse[static_cast<int64_t>(bh) * pNq + tid] * LOG2E : INFINITY;
       }
       named_bar_sync(2, 256);
       mbar_wait(in_full, ph);
@@ -785,6 +807,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(pds_full);
           if (tid == 0) BWD_DBG(4, pair_cnt);
+          if (tid == 224) BWD_DBG(11, pair_cnt);
 
         }
       }

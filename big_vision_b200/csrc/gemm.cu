@@ -459,19 +459,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         named_bar_sync(1, EPI_THREADS);
         if (!OUT_F32 && p_colsum != nullptr && ep_tid < 128) {
           // bias gradient fused into the producer: column sums of the staged (bf16-rounded) tile.
-          // Thread t owns column t % 64 over half of the 128 rows; rows past M hold exact zeros.
-          const int cc = ep_tid & 63, r_lo = (ep_tid >> 6) * 64;
-          const uint32_t cbase = buf + static_cast<uint32_t>(cc & 7) * 2;
-          float csum = 0.f;
-#pragma unroll 8
-          for (int r = r_lo; r < r_lo + 64; ++r) {
-            uint16_t hv;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv)
-                         : "r"(cbase + r * 128 + ((static_cast<uint32_t>(cc >> 3) ^ static_cast<uint32_t>(r & 7)) << 4)));
-            csum += __uint_as_float(static_cast<uint32_t>(hv) << 16);
+          // Warp w sums rows 32w..32w+31, lane l the column pair (2l, 2l+1): each load is one
+          // conflict-free 128-byte row and all 32 are independent.  Rows past M hold exact zeros.
+          const int r_lo = (ep_tid >> 5) * 32;
+          const uint32_t cp = static_cast<uint32_t>(ep_tid & 31);
+          const uint32_t cbase = buf + (cp & 3) * 4;
+          float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int r = r_lo + i;
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w)
+                         : "r"(cbase + r * 128 + (((cp >> 2) ^ static_cast<uint32_t>(r & 7)) << 4)));
+            s0[i & 1] += bf16_lo(w);
+            s1[i & 1] += bf16_hi(w);
           }
-          const int ncol = n0 + c * CH + cc;
-          if (ncol < pN) atomicAdd(p_colsum + ncol, csum);
+          const int ncol = n0 + c * CH + 2 * static_cast<int>(cp);
+          if (ncol < pN) atomicAdd(p_colsum + ncol, s0[0] + s0[1]);
+          if (ncol + 1 < pN) atomicAdd(p_colsum + ncol + 1, s1[0] + s1[1]);
         }
         if (ep_tid == 0) {
           const int c0 = n0 + c * CH;

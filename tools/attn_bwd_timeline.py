@@ -11,7 +11,7 @@ from big_vision_b200 import lib as L  # noqa: E402
 from big_vision_b200 import ops  # noqa: E402
 
 EV = ["c_sdp_full", "c_exp_done", "c_pds_empty", "-", "c_pds_arr", "m_sdp_iss", "m_grad_iss", "c_in_full",
-      "c_stat_rdy", "c_dkv_wait", "c_dkv_full", "c_dq_wait", "c_dq_full", "tma_issued"]
+      "m_pds_full", "m_acc_free", "m_grad_enter", "c_pds_arr_w7", "-", "tma_issued"]
 
 
 def main():
@@ -34,6 +34,14 @@ def main():
   items = B * H
   print(f"N={N} B={B}: {t0.elapsed_time(t1) * 1e3:.1f} us, {items} items, "
         f"{t0.elapsed_time(t1) * 1e3 / (items / 148):.2f} us per item per SM")
+  cs = torch.zeros(3, d, device="cuda")
+  for _ in range(2):
+    ops.attention_bwd(do, q, k, v, o, lse, H, dq_colsum=cs[0], dk_colsum=cs[1], dv_colsum=cs[2])
+  t0.record()
+  ops.attention_bwd(do, q, k, v, o, lse, H, dq_colsum=cs[0], dk_colsum=cs[1], dv_colsum=cs[2])
+  t1.record()
+  torch.cuda.synchronize()
+  print(f"   with fused bias gradients: {t0.elapsed_time(t1) * 1e3:.1f} us")
   buf = (ctypes.c_longlong * 512)()
   lib = L.load()
   lib.bv_debug_attn_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
