@@ -441,6 +441,7 @@ struct BwdDev {
   const bf16* d_o;   // delta = rowsum(O o dO) (element (b,t,h*64+j) at b*bs + t*ld + h*64 + j)
   long long ldo, bso, lddo, bsdo;
   float* dq_colsum; float* dk_colsum; float* dv_colsum;   // optional [H*64] bias gradients
+  int variant;       // BV_BWD_VARIANT (bring-up experiments; 0 = default)
   long long* dbg;    // optional timeline of CTA 0 (BV_ATTN_DBG=1)
 };
 // dbg[256 + slot] : per-pair events (16 per pair, first 12 pairs) of CTA 0
@@ -511,12 +512,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int pH = pin_reg(p.H), pQT = pin_reg(p.QT), pKT = pin_reg(p.KT);
     uint32_t kt_cnt = 0;
+    const int wmode = pin_reg(p.variant) & 3;
     const int pNq = pin_reg(p.Nq), pNk = pin_reg(p.Nk);
-    auto write_tile = [&](uint32_t tcol, const CUtensorMap* tm, int h, int r0, int b, float* colsum, int nvalid) {
+    // release != 0: this is the last tile of an accumulator group; the MMA warp may overwrite the
+    // group as soon as the tile is in registers (staging, column sums and the store are off its
+    // critical path)
+    auto write_tile = [&](uint32_t tcol, const CUtensorMap* tm, int h, int r0, int b, float* colsum, int nvalid,
+                          uint32_t release) {
       uint32_t a[64];
       tmem_ld_32x32b_x32(tmem_base + lane_addr + tcol, *reinterpret_cast<uint32_t(*)[32]>(&a[0]));
       tmem_ld_32x32b_x32(tmem_base + lane_addr + tcol + 32, *reinterpret_cast<uint32_t(*)[32]>(&a[32]));
       tmem_ld_wait();
+      if (release != 0u) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release);
+      }
       if (etid == 0) tma_store_wait_read<0>();
       named_bar_sync(3, 128);
 #pragma unroll
@@ -562,25 +573,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int h = bh % pH, b = bh / pH;
       const uint32_t ph = static_cast<uint32_t>(it) & 1u;
       for (int kt = 0; kt < pKT; ++kt, ++kt_cnt) {
-        mbar_wait(dkv_full, kt_cnt & 1u);
+        mbar_wait_mode(dkv_full, kt_cnt & 1u, wmode);
         tc_fence_after();
-        write_tile(DV_COL, &tmdV, h, kt * TQ, b, p.dv_colsum, pNk);
-        write_tile(DK_COL, &tmdK, h, kt * TQ, b, p.dk_colsum, pNk);
-        // both accumulators are in registers / staged: the MMA warp may start the next key tile
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dkv_empty);
+        write_tile(DV_COL, &tmdV, h, kt * TQ, b, p.dv_colsum, pNk, 0u);
+        write_tile(DK_COL, &tmdK, h, kt * TQ, b, p.dk_colsum, pNk, dkv_empty);
       }
-      mbar_wait(dq_full, ph);
+      mbar_wait_mode(dq_full, ph, wmode);
       tc_fence_after();
-      for (int qt = 0; qt < pQT; ++qt) write_tile(DQ_COL + qt * DH, &tmdQ, h, qt * TQ, b, p.dq_colsum, pNq);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);
+      for (int qt = 0; qt < pQT; ++qt)
+        write_tile(DQ_COL + qt * DH, &tmdQ, h, qt * TQ, b, p.dq_colsum, pNq, qt == pQT - 1 ? dq_empty : 0u);
     }
     if (etid == 0) tma_store_wait<0>();
   } else if (warp >= 8) {
-    reg_dec<40>();
+    reg_dec<48>();
   }
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -622,8 +627,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(sdp_empty, (sdp_cnt & 1u) ^ 1u);
         ++sdp_cnt;
         tc_fence_after();
-        const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
-        const uint32_t va = v_s + kt * TILE_BYTES, da = do_s + qt * TILE_BYTES;
+        uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
+        uint32_t va = v_s + kt * TILE_BYTES, da = do_s + qt * TILE_BYTES;
+        // The addresses are made opaque per call: otherwise the compiler hoists every descriptor
+        // variant of every (kt, qt) out of the item loop and SPILLS them (this thread has few
+        // registers); a spill reload that misses L1 costs more than the MMAs it feeds.
+        asm volatile("" : "+r"(qa), "+r"(ka), "+r"(va), "+r"(da));
         // descriptors are built once per tile; stepping along K only bumps the 16-byte-granular
         // start-address field (this thread issues 32 MMAs per pair -- its instruction count matters)
         const uint64_t dq_k = umma_smem_desc_sw128(qa, 16, 1024), dk_k = umma_smem_desc_sw128(ka, 16, 1024);
@@ -641,8 +650,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // dV, dK, dQ contributions of pair j from the P / dS tiles the compute warps wrote
       auto issue_grads = [&](int j, uint32_t ph) {
         const int kt = j / p.QT, qt = j % p.QT;
-        const uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
-        const uint32_t da = do_s + qt * TILE_BYTES;
+        uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
+        uint32_t da = do_s + qt * TILE_BYTES, pa = p_s, dsa = ds_s;
+        asm volatile("" : "+r"(qa), "+r"(ka), "+r"(da), "+r"(pa), "+r"(dsa));   // see issue_sdp
         BWD_DBG(10, grad_cnt);
         mbar_wait(pds_full, grad_cnt & 1u);
         BWD_DBG(8, grad_cnt);
@@ -651,9 +661,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
         BWD_DBG(9, grad_cnt - 1);
         tc_fence_after();
-        const uint64_t dp_mn = umma_smem_desc_sw128(p_s, TILE_BYTES, 1024);
-        const uint64_t dds_mn = umma_smem_desc_sw128(ds_s, TILE_BYTES, 1024);
-        const uint64_t dds_k = umma_smem_desc_sw128(ds_s, 16, 1024);
+        const uint64_t dp_mn = umma_smem_desc_sw128(pa, TILE_BYTES, 1024);
+        const uint64_t dds_mn = umma_smem_desc_sw128(dsa, TILE_BYTES, 1024);
+        const uint64_t dds_k = umma_smem_desc_sw128(dsa, 16, 1024);
         const uint64_t ddo_mn = umma_smem_desc_sw128(da, 8192, 1024);
         const uint64_t dq_mn = umma_smem_desc_sw128(qa, 8192, 1024);
         const uint64_t dk_mn = umma_smem_desc_sw128(ka, 8192, 1024);
@@ -703,6 +713,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bf16* __restrict__ p_o = pin_reg(p.o);
     const bf16* __restrict__ p_do = pin_reg(p.d_o);
     const long long p_ldo = p.ldo, p_bso = p.bso, p_lddo = p.lddo, p_bsdo = p.bsdo;
+    const int wmode = pin_reg(p.variant) & 3;
     for (int it = 0; it < my_items; ++it) {
       const int bh = blockIdx.x + it * gridDim.x;
       const int h = bh % pH, b = bh / pH;
@@ -744,13 +755,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         lse2_i[tid] = tid < pNq ? p_lse[static_cast<int64_t>(bh) * pNq + tid] * LOG2E : INFINITY;
       }
       named_bar_sync(2, 256);
-      mbar_wait(in_full, ph);
       if (tid == 0) BWD_DBG(7, pair_cnt);
 
       for (int kt = 0; kt < pKT; ++kt) {
         for (int qt = 0; qt < pQT; ++qt, ++pair_cnt) {
           const uint32_t pp = pair_cnt & 1u;
-          mbar_wait(sdp_full, pp);
+          mbar_wait_mode(sdp_full, pp, wmode);
           if (tid == 0) BWD_DBG(0, pair_cnt);
           tc_fence_after();
           const int qrow = qt * TQ + row;
@@ -774,7 +784,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
           if (tid == 0) BWD_DBG(1, pair_cnt);
-          mbar_wait(pds_empty, pp ^ 1u);
+          mbar_wait_mode(pds_empty, pp ^ 1u, wmode);
           if (tid == 0) BWD_DBG(2, pair_cnt);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -914,6 +924,7 @@ int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
     return BV_ERR_INVALID;
   }
   p.dbg = attn_debug_buffer();
+  { const char* e = getenv("BV_BWD_VARIANT"); p.variant = e ? atoi(e) : 0; }
   const int cols = a.H * DH;
   CUtensorMap tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV;
   if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, BWD_ROWS))) return rc;

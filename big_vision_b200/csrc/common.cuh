@@ -134,6 +134,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// variants used to study how waiting warps disturb the tcgen05.mma issuer (see attention.cu):
+// mode bit0: one lane polls, the rest of the warp parks at __syncwarp; bit1: nanosleep between polls
+__device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, int mode) {
+  if (mode == 0) { mbar_wait(bar, parity); return; }
+  if (!(mode & 1) || (threadIdx.x & 31) == 0) {
+    uint32_t ok;
+    for (;;) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      if (ok) break;
+      if (mode & 2) __nanosleep(200);
+    }
+  }
+  if (mode & 1) __syncwarp();
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

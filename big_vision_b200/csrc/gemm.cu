@@ -76,6 +76,7 @@ struct GemmDev {
   const float* bias;
   const bf16* aux;
   float* colsum;         // optional bias-gradient accumulator (bf16 outputs only)
+  long long* dbg;        // optional per-tile timeline of CTA 0 (BV_GEMM_DBG=1)
   long long ldaux;
   int aux_row_mod;
 };
@@ -127,6 +128,13 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 
 // AUXM: how the epilogue's second operand arrives: 0 none, 1 per-thread global loads (row-modulo
 // position embeddings, fp32 outputs), 2 TMA ring in shared memory (residual / gelu' operands)
+// per-tile timeline of CTA 0 (bring-up aid): dbg[tile * 16 + ev] = clock64, first 32 tiles
+#define GEMM_DBG(ev, ti)                                                        \
+  do {                                                                          \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (ti) < 32)                       \
+      p.dbg[(ti) * 16 + (ev)] = clock64();                                      \
+  } while (0)
+
 template <int BN, bool OUT_F32, int EF, int CTAS, int AUXM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -212,6 +220,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int nb0 = n0 + static_cast<int>(cta_rank) * C::B_ROWS;   // this CTA's slice of B
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (kb == kb0) GEMM_DBG(3, (tile - tile_start) / tile_step);
+          if (kb == kb1 - 1) GEMM_DBG(4, (tile - tile_start) / tile_step);
           const uint32_t a_s = base + stage * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_STAGE_BYTES;
           // the pair leader's barrier collects the bytes of both CTAs
@@ -261,10 +271,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int m0, n0, kb0, kb1;
         decode_tile(tile, m0, n0, kb0, kb1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        GEMM_DBG(0, (tile - tile_start) / tile_step);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (kb == kb0) GEMM_DBG(1, (tile - tile_start) / tile_step);
           tc_fence_after();
           const uint32_t a_s = base + stage * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_STAGE_BYTES;
@@ -285,6 +297,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         // accumulator complete: wake the epilogue warps of both CTAs
         if (CTAS == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
+        GEMM_DBG(2, (tile - tile_start) / tile_step);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -355,7 +368,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      if (ep_tid == 0) GEMM_DBG(8, (tile - tile_start) / tile_step);
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (ep_tid == 0) GEMM_DBG(5, (tile - tile_start) / tile_step);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 
@@ -378,6 +393,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (CTAS == 2 && !leader) mbar_arrive_cluster(mapa_cta(tempty_bar(acc), 0));
             else mbar_arrive(tempty_bar(acc));
           }
+          if (ep_tid == 0) GEMM_DBG(6, (tile - tile_start) / tile_step);
         }
         // make sure the TMA store that last used this staging buffer has read it
         if (ep_tid == 0) tma_store_wait_read<1>();
@@ -486,6 +502,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (DUAL) tma_store_2d(&tmD2, buf + OUT_BUF_BYTES, c0, m0);
           }
           tma_store_commit();
+          if (c == NCHUNK - 1) GEMM_DBG(7, (tile - tile_start) / tile_step);
         }
         ++flush;
       }
@@ -507,6 +524,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
   }
+}
+
+static long long* g_gemm_dbg = nullptr;
+long long* gemm_debug_buffer() {
+  static const bool on = [] { const char* e = getenv("BV_GEMM_DBG"); return e && e[0] == '1'; }();
+  if (!on) return nullptr;
+  if (g_gemm_dbg == nullptr && cudaMalloc(&g_gemm_dbg, 32 * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemset(g_gemm_dbg, 0, 32 * 16 * sizeof(long long));
+  return g_gemm_dbg;
 }
 
 template <int BN, bool OUT_F32, int EF, int CTAS, int AUXM>
@@ -563,6 +589,7 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   p.alpha = g.alpha;
   p.bias = g.bias;
   p.colsum = g.colsum;
+  p.dbg = gemm_debug_buffer();
   p.aux = reinterpret_cast<const bf16*>(g.aux);
   p.ldaux = g.ldaux;
   p.aux_row_mod = g.aux_row_mod;
@@ -615,6 +642,14 @@ int dispatch_epi(const GemmArgs& g, cudaStream_t s) {
 }
 
 }  // namespace
+
+int gemm_debug_read(long long* host, int n) {
+  if (g_gemm_dbg == nullptr) return 0;
+  if (n > 32 * 16) n = 32 * 16;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host, g_gemm_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
+}
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) { set_error("bv_gemm: empty problem"); return BV_ERR_INVALID; }

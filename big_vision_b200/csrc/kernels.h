@@ -48,6 +48,7 @@ struct AttnBwdArgs {
   float* delta;                                  // workspace [B, H, Nq]
 };
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
+int gemm_debug_read(long long* host, int n);   // BV_GEMM_DBG=1 timeline of the last GEMM launch
 int attn_debug_read(long long* host, int n);   // BV_ATTN_DBG=1 timeline of the last fwd launch
 
 // ---- element-wise / reductions (elementwise.cu)
