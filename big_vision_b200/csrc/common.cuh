@@ -156,6 +156,18 @@ __device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, in
   }
   if (mode & 1) __syncwarp();
 }
+// one lane of a fully converged warp (the same lane every time for a full mask)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -36,34 +36,54 @@ constexpr int BM = 128;          // rows per CTA
 constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int OUT_BUF_BYTES = BM * 128;      // 128 rows x 128 B
-// epilogue warps: EPI_PARTS warps per TMEM lane quarter, each taking 1/EPI_PARTS of the columns
-// of every staging chunk (more warps = more MUFU / FMA latency hiding in the gelu epilogues)
+// epilogue warps: two per TMEM lane quarter, each taking one half of the tile's columns
 constexpr int EPI_PARTS = 2;
 constexpr int EPI_WARPS = 4 * EPI_PARTS;
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
 
 // epilogue families (template parameter)
 enum : int { EF_BIAS = 0, EF_GELU = 1, EF_RESID = 2, EF_DGELU = 3 };
+
+// Epilogue staging: every epilogue warp owns private 4 KB slabs (32 rows x 128 B, 128B-swizzled)
+// and issues its own TMA loads / stores on them, so the eight warps never synchronise with each
+// other.  Slabs per warp: 1 (plain), 2 (gelu: activation + pre-activation), 3 (ring of the
+// residual / gelu' operand, which is overwritten in place by the result and stored from there).
+constexpr int SLAB_BYTES = 32 * 128;
 
 template <int BN, int CTAS, bool DUAL_OUT, bool AUX_TMA>
 struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;                 // rows of B this CTA loads
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // staging buffers for the TMA stores: 2 (double-buffered), or 2 x 2 when the epilogue
-  // writes two tensors (gelu output + pre-activation)
-  static constexpr int OUT_BUFS = DUAL_OUT ? 4 : 2;
-  // ring of TMA-loaded tiles of the epilogue's second operand (residual / gelu pre-activation)
-  static constexpr int AUX_BUFS = AUX_TMA ? 3 : 0;
-  static constexpr int SMEM_LIMIT = 232448 - 1280;         // 227 KB minus barriers / align slack
-  static constexpr int STAGES_FIT = (SMEM_LIMIT - (OUT_BUFS + AUX_BUFS) * OUT_BUF_BYTES) / STAGE_BYTES;
+  static constexpr int SLABS = AUX_TMA ? 3 : (DUAL_OUT ? 2 : 1);
+  static constexpr int EPI_BYTES = EPI_WARPS * SLABS * SLAB_BYTES;
+  static constexpr int SMEM_LIMIT = 232448 - 1536;         // 227 KB minus barriers / align slack
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;                 // 512 or 256 (power of two)
-  static constexpr int AUX_OFFSET = STAGES * STAGE_BYTES + OUT_BUFS * OUT_BUF_BYTES;
-  static constexpr int BAR_OFFSET = AUX_OFFSET + AUX_BUFS * OUT_BUF_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 512 + 1024;  // + barriers + align slack
+};
+
+// (n tile, m tile, k split) of a persistent CTA's current tile, advanced without divisions
+struct TileIter {
+  int n_tile, m_tile, split;
+  int dn, dm, ds, nn, nm;
+  __device__ __forceinline__ void init(int t0, int step, int num_n, int num_m) {
+    nn = num_n; nm = num_m;
+    n_tile = t0 % nn; int r = t0 / nn; m_tile = r % nm; split = r / nm;
+    dn = step % nn; r = step / nn; dm = r % nm; ds = r / nm;
+  }
+  __device__ __forceinline__ void next() {
+    n_tile += dn;
+    int c = n_tile >= nn ? 1 : 0;
+    n_tile -= c ? nn : 0;
+    m_tile += dm + c;
+    c = m_tile >= nm ? 1 : 0;
+    m_tile -= c ? nm : 0;
+    split += ds + c;
+  }
 };
 
 struct GemmDev {
@@ -146,19 +166,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
 
-  const uint32_t out_buf = base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t epi_base = base + C::EPI_OFFSET;
   const uint32_t bar_base = base + C::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
-  auto aux_full = [&](int b) { return bar_base + 8u * (2 * C::STAGES + 5 + b); };
-  const uint32_t aux_buf0 = base + C::AUX_OFFSET;
+  // per-warp ring of "operand tile landed" barriers (AUXM == 2): warp w, slab b
+  auto aux_full = [&](int w, int b) { return bar_base + 8u * (2 * C::STAGES + 5 + w * 3 + b); };
+  static_assert(8 * (2 * 8 + 5 + EPI_WARPS * 3) <= 512, "barrier region too small");
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(base_ptr + C::BAR_OFFSET + 8 * (2 * C::STAGES + 4));
 
-  const int warp_idx = threadIdx.x >> 5;
+  // broadcast from lane 0 so the compiler can treat the role dispatch as warp-uniform
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -173,7 +195,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 3; ++b) mbar_init(aux_full(b), 1);
+    for (int w = 0; w < EPI_WARPS; ++w)
+      for (int b = 0; b < 3; ++b) mbar_init(aux_full(w, b), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), EPI_WARPS * CTAS);   // one arrive per epilogue warp of each CTA
@@ -198,14 +221,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int tile_start = (CTAS == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = (CTAS == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
-  auto decode_tile = [&](int tile, int& m0, int& n0, int& kb0, int& kb1) {
-    int n_tile = tile % p.num_n_tiles;
-    int rest = tile / p.num_n_tiles;
-    int m_tile = rest % p.num_m_tiles;
-    int split = rest / p.num_m_tiles;
-    m0 = m_tile * (BM * CTAS) + static_cast<int>(cta_rank) * BM;   // this CTA's first row
-    n0 = n_tile * BN;
-    kb0 = split * p.kblocks_per_split;
+  auto tile_coords = [&](const TileIter& it, int& m0, int& n0, int& kb0, int& kb1) {
+    m0 = it.m_tile * (BM * CTAS) + static_cast<int>(cta_rank) * BM;   // this CTA's first row
+    n0 = it.n_tile * BN;
+    kb0 = it.split * p.kblocks_per_split;
     kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
   };
 
@@ -214,14 +233,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
+      TileIter it;
+      it.init(tile_start, tile_step, p.num_n_tiles, p.num_m_tiles);
+      int ti = 0;
+      for (int tile = tile_start; tile < p.total_tiles; tile += tile_step, it.next(), ++ti) {
         int m0, n0, kb0, kb1;
-        decode_tile(tile, m0, n0, kb0, kb1);
+        tile_coords(it, m0, n0, kb0, kb1);
         const int nb0 = n0 + static_cast<int>(cta_rank) * C::B_ROWS;   // this CTA's slice of B
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (kb == kb0) GEMM_DBG(3, (tile - tile_start) / tile_step);
-          if (kb == kb1 - 1) GEMM_DBG(4, (tile - tile_start) / tile_step);
+          if (kb == kb0) GEMM_DBG(3, ti);
+          if (kb == kb1 - 1) GEMM_DBG(4, ti);
           const uint32_t a_s = base + stage * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_STAGE_BYTES;
           // the pair leader's barrier collects the bytes of both CTAs
@@ -259,7 +281,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp_idx == 1) {
     // ========================= MMA issuer (pair leader only) =========================
-    if (lane == 0 && leader) {
+    // The whole warp runs this loop convergently and one elected lane issues the tcgen05
+    // instructions (as CUTLASS does).  Inside a single-lane branch the compiler cannot prove the
+    // descriptors warp-uniform and builds them in vector registers with five R2UR broadcasts per
+    // MMA; convergent code keeps them on the uniform datapath.  It matters: issuing one MMA takes
+    // about as long as the 256 x BN x 16 MMA runs, so this instruction stream IS the tensor pipe's
+    // feed, and everything else it does per tile is kept to a few instructions.
+    if (leader) {
       const uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
@@ -267,54 +295,70 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
-        int m0, n0, kb0, kb1;
-        decode_tile(tile, m0, n0, kb0, kb1);
+      // only the k range of a tile is needed here, and that without divisions
+      const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+      int split = tile_start / tiles_mn, mn = tile_start % tiles_mn;
+      const int dsplit = tile_step / tiles_mn, dmn = tile_step % tiles_mn;
+      int ti = 0;
+      for (int tile = tile_start; tile < p.total_tiles; tile += tile_step, ++ti) {
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        mn += dmn; split += dsplit;
+        if (mn >= tiles_mn) { mn -= tiles_mn; ++split; }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        GEMM_DBG(0, (tile - tile_start) / tile_step);
+        if (lane == 0) GEMM_DBG(0, ti);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          if (kb == kb0) GEMM_DBG(1, (tile - tile_start) / tile_step);
+          if (kb == kb0 && lane == 0) GEMM_DBG(1, ti);
           tc_fence_after();
           const uint32_t a_s = base + stage * C::STAGE_BYTES;
           const uint32_t b_s = a_s + A_STAGE_BYTES;
           const uint64_t adesc0 = umma_smem_desc_sw128(a_s, a_lbo, 1024u);
           const uint64_t bdesc0 = umma_smem_desc_sw128(b_s, b_lbo, 1024u);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // stepping along K only bumps the 16-byte-granular start-address field
-            const uint64_t adesc = adesc0 + k * (a_kstep >> 4);
-            const uint64_t bdesc = bdesc0 + k * (b_kstep >> 4);
-            const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
-            if (CTAS == 2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, accf);
-            else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accf);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // stepping along K only bumps the 16-byte-granular start-address field
+              const uint64_t adesc = adesc0 + k * (a_kstep >> 4);
+              const uint64_t bdesc = bdesc0 + k * (b_kstep >> 4);
+              const uint32_t accf = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (CTAS == 2) umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, accf);
+              else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, accf);
+            }
+            // smem slot free (in both CTAs) once these MMAs retire
+            if (CTAS == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
           }
-          // smem slot free (in both CTAs) once these MMAs retire
-          if (CTAS == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
         // accumulator complete: wake the epilogue warps of both CTAs
-        if (CTAS == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
-        GEMM_DBG(2, (tile - tile_start) / tile_step);
+        if (elect_one()) {
+          if (CTAS == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (lane == 0) GEMM_DBG(2, ti);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ========================= epilogue (8 warps, every CTA) =========================
-    const int ep_tid = threadIdx.x - 64;
+    // ========================= epilogue (8 independent warps, every CTA) =========================
+    // Warp (quarter q, half h) owns rows 32q..32q+31 (its TMEM lanes) x columns [h*BN/2, (h+1)*BN/2)
+    // of the tile, processed in chunks of one 128-byte row (64 bf16 / 32 fp32 columns).  Each chunk:
+    // tcgen05.ld (the next chunk's load is already in flight) -> math in registers -> swizzled
+    // store into the warp's own slab -> TMA store by lane 0.  No CTA-wide barriers: the warps drift
+    // apart and overlap each other's TMEM / MUFU / FMA / shared-memory phases.
+    const int ew = warp_idx - 2;                    // 0..7
     const int quarter = warp_idx & 3;               // TMEM lanes this warp may access
-    const int half = (warp_idx - 2) >> 2;           // which column part of each staging chunk
-    const int row = quarter * 32 + lane;            // row within this CTA's tile == TMEM lane
-    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    const int half = ew >> 2;                       // which half of the tile's columns
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
     constexpr bool DUAL = (EF == EF_GELU);
-    constexpr int CH = OUT_F32 ? 32 : 64;           // columns per staging chunk / TMA store
-    constexpr int WC = CH / EPI_PARTS;              // columns per warp per chunk
-    constexpr int NCHUNK = BN / CH;
+    constexpr int CH = OUT_F32 ? 32 : 64;           // columns per chunk (one 128-byte row)
+    constexpr int WCOLS = BN / EPI_PARTS;           // columns per warp
+    constexpr int NCH = WCOLS / CH;                 // chunks per warp per tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t flush = 0;
     // kernel parameters used per element are copied to registers once (constant-bank reads inside
     // the unrolled column loop would put an LDCU round trip on every group's dependency chain)
     const int pM = pin_reg(p.M), pN = pin_reg(p.N), p_mod = pin_reg(p.aux_row_mod),
@@ -328,64 +372,84 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr bool HAS_AUX = (EF == EF_RESID || EF == EF_DGELU);
     static_assert(!(AUXM == 2) || (HAS_AUX && !OUT_F32), "TMA aux ring is for bf16 residual/gelu' tiles");
     static_assert(HAS_AUX == (AUXM != 0), "aux mode must match the epilogue family");
-    // --- TMA aux ring (AUXM == 2): chunk q of this CTA's epilogue stream lives in buffer q % 3;
-    // thread 0 keeps two chunks in flight ahead of the one being consumed.
-    uint32_t aux_q = 0;                    // chunks consumed so far
-    auto aux_issue = [&](uint32_t q) {     // called by ep_tid 0 only
-      const uint32_t t_iter = q / NCHUNK, c = q % NCHUNK;
-      const int tile = tile_start + static_cast<int>(t_iter) * tile_step;
-      if (tile >= p.total_tiles) return;
+    const uint32_t slab0 = epi_base + static_cast<uint32_t>(ew) * (C::SLABS * SLAB_BYTES);
+    const uint32_t my_row = static_cast<uint32_t>(lane) * 128u;
+
+    TileIter it;
+    it.init(tile_start, tile_step, p.num_n_tiles, p.num_m_tiles);
+    // --- AUXM == 2: lane 0 keeps the operand box of the NEXT chunk in flight (ring of 3 slabs)
+    uint32_t aux_q = 0;                    // chunks consumed so far by this warp
+    TileIter it_nx = it;                   // tile of chunk aux_q + 1
+    int c_nx = 0, tile_nx = tile_start;
+    auto aux_issue_next = [&]() {          // lane 0: load the box of chunk (tile_nx, c_nx) into slab (aux_q+1)%3
+      if (tile_nx >= p.total_tiles) return;
       int m0, n0, kb0, kb1;
-      decode_tile(tile, m0, n0, kb0, kb1);
-      const uint32_t b = q % 3u;
-      mbar_expect_tx(aux_full(b), OUT_BUF_BYTES);
-      tma_load_2d(aux_buf0 + b * OUT_BUF_BYTES, &tmAux, aux_full(b), n0 + static_cast<int>(c) * CH, m0);
+      tile_coords(it_nx, m0, n0, kb0, kb1);
+      const uint32_t b = (aux_q + 1u) % 3u;
+      mbar_expect_tx(aux_full(ew, b), SLAB_BYTES);
+      tma_load_2d(slab0 + b * SLAB_BYTES, &tmAux, aux_full(ew, b), n0 + half * WCOLS + c_nx * CH,
+                  m0 + quarter * 32);
     };
-    if (AUXM == 2 && ep_tid == 0) { aux_issue(0); aux_issue(1); }
-    for (int tile = tile_start; tile < p.total_tiles; tile += tile_step) {
+    auto aux_advance = [&]() {             // move (tile_nx, c_nx) one chunk forward
+      if (++c_nx == NCH) { c_nx = 0; tile_nx += tile_step; it_nx.next(); }
+    };
+    if (AUXM == 2 && lane == 0) {
+      // chunk 0 goes to slab 0: same code path with aux_q "= -1"
       int m0, n0, kb0, kb1;
-      decode_tile(tile, m0, n0, kb0, kb1);
-      const int grow = m0 + row;
+      tile_coords(it_nx, m0, n0, kb0, kb1);
+      if (tile_nx < p.total_tiles) {
+        mbar_expect_tx(aux_full(ew, 0), SLAB_BYTES);
+        tma_load_2d(slab0, &tmAux, aux_full(ew, 0), n0 + half * WCOLS, m0 + quarter * 32);
+      }
+    }
+    if (AUXM == 2) aux_advance();
+
+    int ti = 0;
+    for (int tile = tile_start; tile < p.total_tiles; tile += tile_step, it.next(), ++ti) {
+      int m0, n0, kb0, kb1;
+      tile_coords(it, m0, n0, kb0, kb1);
+      const int grow0 = m0 + quarter * 32;          // first row of this warp's boxes
+      const int grow = grow0 + lane;
       const bool row_ok = grow < pM;
-      // AUXM == 1: the residual / position-embedding operand of this thread's row for the WHOLE
-      // tile is fetched before waiting for the accumulator.
-      constexpr int NAUX = (AUXM == 1) ? NCHUNK * (WC / 8) : 1;
-      uint4 aq_all[NAUX];
-      if (AUXM == 1) {
-        const bf16* aux_row = nullptr;
-        if (row_ok) {
-          long long ar = p_mod > 0 ? (grow % p_mod) : grow;
-          aux_row = p_aux + ar * p_ldaux;
-        }
+      const int wcol0 = n0 + half * WCOLS;          // first column of this warp
+      const bf16* aux_row = nullptr;                // AUXM == 1: this thread's row of the operand
+      if (AUXM == 1 && row_ok) {
+        const long long ar = p_mod > 0 ? (grow % p_mod) : grow;
+        aux_row = p_aux + ar * p_ldaux;
+      }
+      if (ew == 0 && lane == 0) GEMM_DBG(8, ti);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      if (ew == 0 && lane == 0) GEMM_DBG(5, ti);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * WCOLS;
+
+      // TMEM is read in units of 32 columns, double-buffered in registers: unit u+1 is in flight
+      // while unit u is processed
+      constexpr int UPC = CH / 32;                  // units per chunk (2 for bf16, 1 for fp32)
+      constexpr int NU = NCH * UPC;                 // units per tile
+      constexpr int GPU_ = 4;                       // 8-column groups per unit
+      uint32_t rbuf[2][32];
+      tmem_ld_32x32b_x32(t_row, rbuf[0]);
+      uint32_t slab = slab0;
 #pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
+      for (int u = 0; u < NU; ++u) {
+        const int c = u / UPC, uc = u % UPC;        // chunk, unit within the chunk
+        uint32_t (&r)[32] = rbuf[u & 1];
+        const int ncol0 = wcol0 + c * CH;           // first column of the chunk
+        // AUXM == 1: fetch this unit's operand before blocking on the accumulator
+        uint4 aq[(AUXM == 1) ? GPU_ : 1];
+        if (AUXM == 1) {
 #pragma unroll
-          for (int g = 0; g < WC / 8; ++g) {
-            const int nc = n0 + c * CH + half * WC + g * 8;
-            aq_all[c * (WC / 8) + g] = make_uint4(0u, 0u, 0u, 0u);
-            if (aux_row != nullptr && nc < pN)
-              aq_all[c * (WC / 8) + g] = *reinterpret_cast<const uint4*>(aux_row + nc);
+          for (int g = 0; g < GPU_; ++g) {
+            const int nc = ncol0 + uc * 32 + g * 8;
+            aq[g] = make_uint4(0u, 0u, 0u, 0u);
+            if (aux_row != nullptr && nc < pN) aq[g] = *reinterpret_cast<const uint4*>(aux_row + nc);
           }
         }
-      }
-      if (ep_tid == 0) GEMM_DBG(8, (tile - tile_start) / tile_step);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      if (ep_tid == 0) GEMM_DBG(5, (tile - tile_start) / tile_step);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        // double-buffered staging: one buffer (or one act/pre pair) per in-flight TMA store
-        const uint32_t buf = out_buf + (flush & 1u) * (DUAL ? 2 : 1) * OUT_BUF_BYTES;
-        const int col_t = c * CH + half * WC;       // first column (within the tile) of this warp
-        const int ncol0 = n0 + col_t;
-        uint32_t r[WC];
-        if constexpr (WC == 32) tmem_ld_32x32b_x32(t_row + col_t, r);
-        else if constexpr (WC == 16) tmem_ld_32x32b_x16(t_row + col_t, r);
-        else tmem_ld_32x32b_x8(t_row + col_t, r);
         tmem_ld_wait();
-        if (c == NCHUNK - 1) {
+        if (u + 1 < NU) {
+          tmem_ld_32x32b_x32(t_row + (u + 1) * 32, rbuf[(u + 1) & 1]);
+        } else {
           // accumulator fully drained into registers -> hand TMEM back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -393,22 +457,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (CTAS == 2 && !leader) mbar_arrive_cluster(mapa_cta(tempty_bar(acc), 0));
             else mbar_arrive(tempty_bar(acc));
           }
-          if (ep_tid == 0) GEMM_DBG(6, (tile - tile_start) / tile_step);
+          if (ew == 0 && lane == 0) GEMM_DBG(6, ti);
         }
-        // make sure the TMA store that last used this staging buffer has read it
-        if (ep_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, EPI_THREADS);
-        uint32_t aux_s = 0;
-        if (AUXM == 2) {
-          // every thread is past chunk q-1 (barrier above), so its buffer can be refilled with q+2
-          if (ep_tid == 0) aux_issue(aux_q + 2);
-          mbar_wait(aux_full(aux_q % 3u), (aux_q / 3u) & 1u);
-          aux_s = aux_buf0 + (aux_q % 3u) * OUT_BUF_BYTES + row * 128;
+        if (uc == 0 && AUXM == 2) {
+          // chunk start: which slab holds this chunk's operand (the result overwrites it in place)
+          if (lane == 0) {
+            // slab (aux_q+1)%3 was last stored from two chunks ago: allow only the newest store
+            // to be still reading, then refill it with the next chunk's operand
+            tma_store_wait_read<1>();
+            aux_issue_next();
+          }
+          aux_advance();
+          slab = slab0 + (aux_q % 3u) * SLAB_BYTES;
+          mbar_wait(aux_full(ew, aux_q % 3u), (aux_q / 3u) & 1u);
           ++aux_q;
         }
+        uint32_t ow[DUAL ? 2 : 1][OUT_F32 ? 32 : 16];   // packed results of this unit
 #pragma unroll
-        for (int g = 0; g < WC / 8; ++g) {      // 8 columns per group
-          const int nc = ncol0 + g * 8;
+        for (int g = 0; g < GPU_; ++g) {    // 8 columns per group
+          const int nc = ncol0 + uc * 32 + g * 8;
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
@@ -433,11 +500,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else if (EF == EF_RESID || EF == EF_DGELU) {
             uint4 q;
             if (AUXM == 2) {
-              const uint32_t pc = static_cast<uint32_t>(half * (WC / 8) + g);
+              const uint32_t piece = static_cast<uint32_t>(uc * 4 + g);
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(aux_s + ((pc ^ sw) << 4)));
+                           : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                           : "r"(slab + my_row + ((piece ^ sw) << 4)));
             } else {
-              q = aq_all[c * (WC / 8) + g];
+              q = aq[(AUXM == 1) ? g : 0];
             }
             const float a[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                 bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
@@ -450,65 +518,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           if (OUT_F32) {
-            const uint32_t p0 = static_cast<uint32_t>(half * (WC / 4) + g * 2), p1 = p0 + 1;
-            const uint32_t a0 = buf + row * 128 + ((p0 ^ sw) << 4);
-            const uint32_t a1 = buf + row * 128 + ((p1 ^ sw) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "f"(v[0]),
-                         "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a1), "f"(v[4]),
-                         "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ow[0][(OUT_F32 ? g * 8 : 0) + i] = __float_as_uint(v[i]);
           } else {
-            const uint32_t piece = static_cast<uint32_t>(half * (WC / 8) + g);
-            const uint32_t a0 = buf + row * 128 + ((piece ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0),
-                         "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
-                         "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ow[0][g * 4 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
             if (DUAL) {
-              const uint32_t a2 = a0 + OUT_BUF_BYTES;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a2),
-                           "r"(pack_bf16(v2[0], v2[1])), "r"(pack_bf16(v2[2], v2[3])),
-                           "r"(pack_bf16(v2[4], v2[5])), "r"(pack_bf16(v2[6], v2[7])) : "memory");
+#pragma unroll
+              for (int i = 0; i < 4; ++i) ow[DUAL ? 1 : 0][g * 4 + i] = pack_bf16(v2[2 * i], v2[2 * i + 1]);
             }
           }
         }
-        fence_proxy_async();
-        named_bar_sync(1, EPI_THREADS);
-        if (!OUT_F32 && p_colsum != nullptr && ep_tid < 128) {
-          // bias gradient fused into the producer: column sums of the staged (bf16-rounded) tile.
-          // Warp w sums rows 32w..32w+31, lane l the column pair (2l, 2l+1): each load is one
-          // conflict-free 128-byte row and all 32 are independent.  Rows past M hold exact zeros.
-          const int r_lo = (ep_tid >> 5) * 32;
-          const uint32_t cp = static_cast<uint32_t>(ep_tid & 31);
-          const uint32_t cbase = buf + (cp & 3) * 4;
-          float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
+        // the slab must have been read by the TMA store of the previous chunk (the math above has
+        // given it time); the AUXM == 2 ring was already checked when its operand was requested
+        if (uc == 0 && AUXM != 2) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        constexpr int PIECES = OUT_F32 ? 8 : 4;     // 16-byte pieces this unit contributes to the row
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int r = r_lo + i;
-            uint32_t w;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w)
-                         : "r"(cbase + r * 128 + (((cp >> 2) ^ static_cast<uint32_t>(r & 7)) << 4)));
-            s0[i & 1] += bf16_lo(w);
-            s1[i & 1] += bf16_hi(w);
+        for (int j = 0; j < PIECES; ++j) {
+          const uint32_t piece = static_cast<uint32_t>(uc * PIECES + j);
+          const uint32_t a0 = slab + my_row + ((piece ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0), "r"(ow[0][j * 4]),
+                       "r"(ow[0][j * 4 + 1]), "r"(ow[0][j * 4 + 2]), "r"(ow[0][j * 4 + 3]) : "memory");
+          if (DUAL) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a0 + SLAB_BYTES),
+                         "r"(ow[DUAL ? 1 : 0][j * 4]), "r"(ow[DUAL ? 1 : 0][j * 4 + 1]),
+                         "r"(ow[DUAL ? 1 : 0][j * 4 + 2]), "r"(ow[DUAL ? 1 : 0][j * 4 + 3]) : "memory");
           }
-          const int ncol = n0 + c * CH + 2 * static_cast<int>(cp);
-          if (ncol < pN) atomicAdd(p_colsum + ncol, s0[0] + s0[1]);
-          if (ncol + 1 < pN) atomicAdd(p_colsum + ncol + 1, s1[0] + s1[1]);
         }
-        if (ep_tid == 0) {
-          const int c0 = n0 + c * CH;
-          if (c0 < pN) {
-            if (p_reduce) tma_reduce_add_2d(&tmD, buf, c0, m0);
-            else tma_store_2d(&tmD, buf, c0, m0);
-            if (DUAL) tma_store_2d(&tmD2, buf + OUT_BUF_BYTES, c0, m0);
+        if (uc == UPC - 1) {
+          // chunk complete: publish the slab to the async proxy and store it
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (ncol0 < pN) {
+              if (p_reduce) tma_reduce_add_2d(&tmD, slab, ncol0, grow0);
+              else tma_store_2d(&tmD, slab, ncol0, grow0);
+              if (DUAL) tma_store_2d(&tmD2, slab + SLAB_BYTES, ncol0, grow0);
+            }
+            tma_store_commit();
+            if (ew == 0 && u == NU - 1) GEMM_DBG(7, ti);
           }
-          tma_store_commit();
-          if (c == NCHUNK - 1) GEMM_DBG(7, (tile - tile_start) / tile_step);
+          if (!OUT_F32 && p_colsum != nullptr) {
+            // bias gradient fused into the producer: column sums of the staged (bf16-rounded) slab.
+            // Lane l sums the column pair (2l, 2l+1) over the warp's 32 rows: every load is one
+            // conflict-free 128-byte row and all 32 are independent.  Rows past M hold exact zeros.
+            const uint32_t cp = static_cast<uint32_t>(lane);
+            const uint32_t cbase = slab + (cp & 3) * 4;
+            float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w)
+                           : "r"(cbase + i * 128 + (((cp >> 2) ^ static_cast<uint32_t>(i & 7)) << 4)));
+              s0[i & 1] += bf16_lo(w);
+              s1[i & 1] += bf16_hi(w);
+            }
+            const int ncol = ncol0 + 2 * lane;
+            if (ncol < pN) atomicAdd(p_colsum + ncol, s0[0] + s0[1]);
+            if (ncol + 1 < pN) atomicAdd(p_colsum + ncol + 1, s1[0] + s1[1]);
+          }
         }
-        ++flush;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (ep_tid == 0) tma_store_wait<0>();
+    if (lane == 0) tma_store_wait<0>();
   }
 
   __syncwarp();
@@ -547,17 +623,18 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   if (g.b_mn) rc = make_tmap_2d(&tmB, bf, g.B, g.N, g.K, g.ldb * 2, 64, 64);
   else        rc = make_tmap_2d(&tmB, bf, g.B, g.K, g.N, g.ldb * 2, 64, C::B_ROWS);
   if (rc) return rc;
-  if (OUT_F32) rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, g.D, g.N, g.M, g.ldd * 4, 32, BM);
-  else         rc = make_tmap_2d(&tmD, bf, g.D, g.N, g.M, g.ldd * 2, 64, BM);
+  // epilogue boxes: one warp's 32 rows x one 128-byte row of columns
+  if (OUT_F32) rc = make_tmap_2d(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, g.D, g.N, g.M, g.ldd * 4, 32, 32);
+  else         rc = make_tmap_2d(&tmD, bf, g.D, g.N, g.M, g.ldd * 2, 64, 32);
   if (rc) return rc;
   tmD2 = tmD;
   tmAux = tmD;
   if (AUXM == 2) {
-    rc = make_tmap_2d(&tmAux, bf, g.aux, g.N, g.M, g.ldaux * 2, 64, BM);
+    rc = make_tmap_2d(&tmAux, bf, g.aux, g.N, g.M, g.ldaux * 2, 64, 32);
     if (rc) return rc;
   }
   if (EF == EF_GELU) {
-    rc = make_tmap_2d(&tmD2, bf, g.D2, g.N, g.M, g.ldd2 * 2, 64, BM);
+    rc = make_tmap_2d(&tmD2, bf, g.D2, g.N, g.M, g.ldd2 * 2, 64, 32);
     if (rc) return rc;
   }
 
