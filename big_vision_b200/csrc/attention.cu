@@ -302,27 +302,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     } else if (warp == 9) {
       // ---------------- S = Q K^T issuer ----------------
-      if (lane == 0) {
+      // The MMA issuers run as whole, converged warps and one elected lane executes the tcgen05
+      // instructions: inside a single-lane branch the compiler cannot prove the descriptors
+      // warp-uniform and wraps EVERY tcgen05.mma in an elect loop with four R2UR broadcasts, which
+      // makes the issue (not the tensor pipe) the limit for these small MMAs.
+      {
         const uint32_t idesc_s = umma_idesc_bf16(128, p.NKP, 0, 0);   // both operands K-major
         for (int i = 0; i < my_tiles; ++i) {
           const int st = i % p.nstage, bf = i % p.nbuf;
           mbar_wait(in_full(st), static_cast<uint32_t>(i / p.nstage) & 1u);
           mbar_wait(s_empty(bf), (static_cast<uint32_t>(i / p.nbuf) & 1u) ^ 1u);
           tc_fence_after();
-          ATTN_DBG(1, i);
+          if (lane == 0) ATTN_DBG(1, i);
           const uint32_t q_s = base + st * L.stage_bytes;
           const uint32_t k_s = q_s + TILE_BYTES;
           const uint32_t d = tmem_base + bf * p.NKP;
           const uint64_t dq = umma_smem_desc_sw128(q_s, 16, 1024), dk = umma_smem_desc_sw128(k_s, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(d, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(s_full(bf));
-          ATTN_DBG(2, i);
+            for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(d, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(s_full(bf));
+          }
+          __syncwarp();
+          if (lane == 0) ATTN_DBG(2, i);
         }
       }
     } else if (warp == 10) {
-      // ---------------- O = P V issuer (its own thread: never blocked behind a TMA wait) --------
-      if (lane == 0) {
+      // ---------------- O = P V issuer (its own warp: never blocked behind a TMA wait) --------
+      {
         const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);      // V is MN-major
         const int ksteps = p.NKP / 16;
         for (int i = 0; i < my_tiles; ++i) {
@@ -330,17 +337,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_wait(p_full, static_cast<uint32_t>(i) & 1u);
           mbar_wait(o_empty, (static_cast<uint32_t>(i) & 1u) ^ 1u);
           tc_fence_after();
-          ATTN_DBG(7, i);
+          if (lane == 0) ATTN_DBG(7, i);
           const uint32_t v_s = base + st * L.stage_bytes + TILE_BYTES + L.kv_bytes;
           const uint32_t p_s = base + L.p_off;
           const uint64_t dpd = umma_smem_desc_sw128(p_s, 16, 1024), dvd = umma_smem_desc_sw128(v_s, 8192, 1024);
-          for (int j = 0; j < ksteps; ++j)
-            umma_bf16_ss(tmem_base + O_COL, dpd + (j >> 2) * (TILE_BYTES / 16) + (j & 3) * 2, dvd + j * 128,
-                         idesc_o, j > 0 ? 1u : 0u);
-          umma_commit(o_full);
-          umma_commit(p_empty);
-          ATTN_DBG(8, i);
-          umma_commit(in_empty(st));   // Q/K were consumed by S(i) long before (softmax(i) waited on it)
+          if (elect_one()) {
+            for (int j = 0; j < ksteps; ++j)
+              umma_bf16_ss(tmem_base + O_COL, dpd + (j >> 2) * (TILE_BYTES / 16) + (j & 3) * 2, dvd + j * 128,
+                           idesc_o, j > 0 ? 1u : 0u);
+            umma_commit(o_full);
+            umma_commit(p_empty);
+            umma_commit(in_empty(st));   // Q/K were consumed by S(i) long before (softmax(i) waited on it)
+          }
+          __syncwarp();
+          if (lane == 0) ATTN_DBG(8, i);
         }
       }
     }
@@ -614,8 +624,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (whole warp converged, one elected lane issues; see the forward) ----
+    {
       const uint32_t id_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
       const uint32_t id_mm = umma_idesc_bf16(128, DH, 1, 1);    // dV, dK : A^T (MN) x B (MN)
       const uint32_t id_km = umma_idesc_bf16(128, DH, 0, 1);    // dQ     : A (K)  x B (MN)
@@ -639,13 +649,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t ddo_k = umma_smem_desc_sw128(da, 16, 1024), dv_k = umma_smem_desc_sw128(va, 16, 1024);
         // S and dP are independent accumulators: interleaving their K steps keeps two dependent
         // chains in flight (an MMA that accumulates into the tile of the previous one waits for it)
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_bf16_ss(tmem_base + S_COL, dq_k + k * 2, dk_k + k * 2, id_kk, k > 0 ? 1u : 0u);
-          umma_bf16_ss(tmem_base + DP_COL, ddo_k + k * 2, dv_k + k * 2, id_kk, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_ss(tmem_base + S_COL, dq_k + k * 2, dk_k + k * 2, id_kk, k > 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_base + DP_COL, ddo_k + k * 2, dv_k + k * 2, id_kk, k > 0 ? 1u : 0u);
+          }
+          umma_commit(sdp_full);
         }
-        umma_commit(sdp_full);
-        BWD_DBG(5, sdp_cnt - 1);
+        __syncwarp();
+        if (lane == 0) BWD_DBG(5, sdp_cnt - 1);
       };
       // dV, dK, dQ contributions of pair j from the P / dS tiles the compute warps wrote
       auto issue_grads = [&](int j, uint32_t ph) {
@@ -653,13 +666,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t qa = q_s + qt * TILE_BYTES, ka = k_s + kt * TILE_BYTES;
         uint32_t da = do_s + qt * TILE_BYTES, pa = p_s, dsa = ds_s;
         asm volatile("" : "+r"(qa), "+r"(ka), "+r"(da), "+r"(pa), "+r"(dsa));   // see issue_sdp
-        BWD_DBG(10, grad_cnt);
+        if (lane == 0) BWD_DBG(10, grad_cnt);
         mbar_wait(pds_full, grad_cnt & 1u);
-        BWD_DBG(8, grad_cnt);
+        if (lane == 0) BWD_DBG(8, grad_cnt);
         ++grad_cnt;
         if (qt == 0) mbar_wait(dkv_empty, (kt_cnt & 1u) ^ 1u);
         if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
-        BWD_DBG(9, grad_cnt - 1);
+        if (lane == 0) BWD_DBG(9, grad_cnt - 1);
         tc_fence_after();
         const uint64_t dp_mn = umma_smem_desc_sw128(pa, TILE_BYTES, 1024);
         const uint64_t dds_mn = umma_smem_desc_sw128(dsa, TILE_BYTES, 1024);
@@ -668,19 +681,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t dq_mn = umma_smem_desc_sw128(qa, 8192, 1024);
         const uint64_t dk_mn = umma_smem_desc_sw128(ka, 8192, 1024);
         // three independent accumulation chains (dV, dK, dQ) issued round-robin
+        const bool last_q = (qt == p.QT - 1);
+        if (elect_one()) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const uint32_t accv = (qt > 0 || jj > 0) ? 1u : 0u;
-          // dV, dK: contraction over the 128 query rows, 16 per step (2048 B in the MN-major tiles)
-          umma_bf16_ss(tmem_base + DV_COL, dp_mn + jj * 128, ddo_mn + jj * 128, id_mm, accv);
-          umma_bf16_ss(tmem_base + DK_COL, dds_mn + jj * 128, dq_mn + jj * 128, id_mm, accv);
-          // dQ: contraction over the 128 keys
-          umma_bf16_ss(tmem_base + DQ_COL + qt * DH, dds_k + (jj >> 2) * (TILE_BYTES / 16) + (jj & 3) * 2,
-                       dk_mn + jj * 128, id_km, (kt > 0 || jj > 0) ? 1u : 0u);
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint32_t accv = (qt > 0 || jj > 0) ? 1u : 0u;
+            // dV, dK: contraction over the 128 query rows, 16 per step (2048 B in the MN-major tiles)
+            umma_bf16_ss(tmem_base + DV_COL, dp_mn + jj * 128, ddo_mn + jj * 128, id_mm, accv);
+            umma_bf16_ss(tmem_base + DK_COL, dds_mn + jj * 128, dq_mn + jj * 128, id_mm, accv);
+            // dQ: contraction over the 128 keys
+            umma_bf16_ss(tmem_base + DQ_COL + qt * DH, dds_k + (jj >> 2) * (TILE_BYTES / 16) + (jj & 3) * 2,
+                         dk_mn + jj * 128, id_km, (kt > 0 || jj > 0) ? 1u : 0u);
+          }
+          umma_commit(pds_empty);
+          if (last_q) umma_commit(dkv_full);
         }
-        umma_commit(pds_empty);
-        BWD_DBG(6, grad_cnt - 1);
-        if (qt == p.QT - 1) { umma_commit(dkv_full); ++kt_cnt; }
+        __syncwarp();
+        if (lane == 0) BWD_DBG(6, grad_cnt - 1);
+        if (last_q) ++kt_cnt;
       };
       for (int it = 0; it < my_items; ++it) {
         const uint32_t ph = static_cast<uint32_t>(it) & 1u;
@@ -692,8 +710,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (j + 1 < pairs) issue_sdp(j + 1);
           issue_grads(j, ph);
         }
-        umma_commit(dq_full);
-        umma_commit(in_empty);
+        if (elect_one()) {
+          umma_commit(dq_full);
+          umma_commit(in_empty);
+        }
+        __syncwarp();
       }
     }
   } else if (warp < 8) {
