@@ -29,6 +29,8 @@ OPT_CONFIG = dict(optax_name="scale_by_adam", optax=dict(b2=0.95, mu_dtype="bflo
 RES, TXT_LEN = 224, 64
 # algorithmic training FLOPs per image-text pair (3 x forward; SURVEY.md 8d / BASELINE.md 3)
 FLOPS_PER_PAIR = 139.3e9
+# ncu-measured DRAM traffic per GEMM launch (all GEMM launches of one bench run, see profiles/)
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 0.927e9
 
 
 def measured_peaks():
@@ -207,7 +209,7 @@ def run_ours(args):
   if rank == 0:
     sampler.start()
   ops_gemm = ops.gemm
-  gemm_events, gemm_flops = [], [0.0]
+  gemm_events, gemm_flops, gemm_bytes = [], [0.0], [0.0]
 
   def timed_gemm(a, b, **kw):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -219,6 +221,12 @@ def run_ours(args):
     K = a.shape[0] if a_mn else a.shape[1]
     N = b.shape[1] if b_mn else b.shape[0]
     gemm_flops[0] += 2.0 * M * N * K
+    # algorithmic bytes of this launch: both operands once, every output once, the epilogue operand
+    o = out[0] if isinstance(out, tuple) else out
+    nbytes = 2.0 * K * (M + N) + M * N * o.element_size() * (2 if isinstance(out, tuple) else 1)
+    if kw.get("aux") is not None:
+      nbytes += 2.0 * M * N if not kw.get("aux_row_mod") else 2.0 * kw["aux_row_mod"] * N
+    gemm_bytes[0] += nbytes
     gemm_events.append((e0, e1))
     return out
 
@@ -320,7 +328,14 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 persistent GEMM)",
                      "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
-                     "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained",
+                     # per launch, averaged over the step's GEMM launches (shapes differ)
+                     "launches_per_step": len(gemm_events) // args.steps,
+                     "flop_per_launch": gemm_flops[0] / len(gemm_events),
+                     "algorithmic_bytes_per_launch": gemm_bytes[0] / len(gemm_events),
+                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the GEMM "
+                                       "launches of profiles/r01_final_launch_summary.md",
                      "gemm_share_of_step": gemm_ms / ms,
                      "step_mfu": value / world * FLOPS_PER_PAIR / 1e12 / peak_tf},
         "cpu_baseline": cpu,
