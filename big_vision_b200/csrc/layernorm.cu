@@ -91,6 +91,76 @@ ln_fwd_kernel(const void* __restrict__ x, int x_dt, const float* __restrict__ sc
   }
 }
 
+// bf16 -> bf16 streaming forward: persistent warps walk the rows with a grid stride, keep scale and
+// bias in registers (re-reading them per row costs 4x the L1 traffic of the row itself) and keep
+// the load of the next row in flight while the current one is reduced and written.
+template <int NCH>
+__global__ void __launch_bounds__(LN_THREADS, 2)
+ln_fwd_stream_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                     const float* __restrict__ bias, bf16* __restrict__ y,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int d,
+                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nchunks = d >> 3;
+  float g[NCH][8], b[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { g[i][j] = 0.f; b[i][j] = 0.f; }
+    if (c < nchunks) { load8f(scale + c * 8, g[i]); load8f(bias + c * 8, b[i]); }
+  }
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * LN_WARPS;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
+  const float inv_d = 1.0f / static_cast<float>(d);
+  uint4 buf[2][NCH];
+  auto fetch = [&](int64_t row, uint4 (&q)[NCH]) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      q[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < rows && c < nchunks) q[i] = ld_nc_na(reinterpret_cast<const uint4*>(x + row * d + c * 8));
+    }
+  };
+  auto process = [&](int64_t row, uint4 (&q)[NCH]) {
+    float v[NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      v[i][0] = bf16_lo(q[i].x); v[i][1] = bf16_hi(q[i].x); v[i][2] = bf16_lo(q[i].y); v[i][3] = bf16_hi(q[i].y);
+      v[i][4] = bf16_lo(q[i].z); v[i][5] = bf16_hi(q[i].z); v[i][6] = bf16_lo(q[i].w); v[i][7] = bf16_hi(q[i].w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1 += v[i][j]; s2 += v[i][j] * v[i][j]; }   // padded chunks are zero
+    }
+    fetch(row + 2 * stride, q);        // this buffer is free again: refill it two rows ahead
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const float mean = s1 * inv_d;
+    const float var = fmaxf(s2 * inv_d - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[i][j] + b[i][j];
+        store8(y, DT_BF16, row * d + c * 8, o);
+      }
+    }
+  };
+  fetch(row0, buf[0]);
+  fetch(row0 + stride, buf[1]);
+  for (int64_t row = row0; row < rows; row += 2 * stride) {
+    process(row, buf[0]);
+    if (row + stride < rows) process(row + stride, buf[1]);
+  }
+}
+
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * scale
 // dscale += sum_rows dy * xhat ; dbias += sum_rows dy ; dx_colsum += sum_rows dx
 template <int NCH>
@@ -195,7 +265,9 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_dt, const void* __restrict__ x
 // arithmetic.  Memory-level parallelism then no longer depends on registers: 8 warps x
 // (DEPTH-1) rows x 4.5 KB are in flight per SM, enough to cover HBM latency.
 // ---------------------------------------------------------------------------
-constexpr int LNP_DEPTH = 4;
+constexpr int LNP_DEPTH = 3;
+constexpr int LNP_THREADS = 384;        // 12 warps: the kernel is issue-bound, more warps = more IPC
+constexpr int LNP_WARPS = LNP_THREADS / 32;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -216,7 +288,7 @@ __device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
 }
 
 template <int NCH, bool HAS_RES>
-__global__ void __launch_bounds__(LN_THREADS, 1)
+__global__ void __launch_bounds__(LNP_THREADS, 1)
 ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    const float* __restrict__ scale, const float* __restrict__ mean_in,
                    const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
@@ -231,7 +303,7 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   float* red = reinterpret_cast<float*>(smem_ln);                       // [3][d]
   const int row_bytes = d * 2;
   const uint32_t ring = smem_u32(smem_ln) + 3 * d * 4 + warp * (LNP_DEPTH * NARR * row_bytes);
-  for (int i = threadIdx.x; i < 3 * d; i += LN_THREADS) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * d; i += LNP_THREADS) red[i] = 0.f;
   __syncthreads();
 
   float acc_g[NCH][8], acc_b[NCH][8], acc_c[NCH][8];
@@ -244,8 +316,8 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     if (c < nchunks) load8f(scale + c * 8, g[i]);
   }
   const float inv_d = 1.0f / static_cast<float>(d);
-  const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * LN_WARPS;
-  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * LN_WARPS + warp;
+  const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * LNP_WARPS;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * LNP_WARPS + warp;
 
   auto issue = [&](int64_t row, int slot) {
     if (row < rows) {
@@ -273,22 +345,28 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     cp_async_wait<LNP_DEPTH - 1>();
     __syncwarp();
     const float mean = mean_in[row], rstd = rstd_in[row];
+    const float nmr = -mean * rstd;
     const uint32_t sbase = ring + slot * (NARR * row_bytes);
     float c1 = 0.f, c2 = 0.f;
+    // xhat and g = dy * scale stay in registers between the two passes (the kernel is bound by
+    // instruction issue, not by HBM: re-reading and re-converting them costs a fifth of its time)
+    float xh[NCH][8], gy[NCH][8];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = lane + 32 * i;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; gy[i][j] = 0.f; }
       if (c < nchunks) {
         float xv[8], dv[8];
         lds8(sbase + c * 16, xv);
         lds8(sbase + row_bytes + c * 16, dv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mean) * rstd;
-          const float gy = dv[j] * g[i][j];
-          c1 += gy;
-          c2 += gy * xh;
-          acc_g[i][j] += dv[j] * xh;
+          xh[i][j] = fmaf(xv[j], rstd, nmr);
+          gy[i][j] = dv[j] * g[i][j];
+          c1 += gy[i][j];
+          c2 = fmaf(gy[i][j], xh[i][j], c2);
+          acc_g[i][j] = fmaf(dv[j], xh[i][j], acc_g[i][j]);
           acc_b[i][j] += dv[j];
         }
       }
@@ -299,24 +377,18 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     for (int i = 0; i < NCH; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunks) {
-        float xv[8], dv[8], o[8];
-        lds8(sbase + c * 16, xv);
-        lds8(sbase + row_bytes + c * 16, dv);
+        float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mean) * rstd;
-          o[j] = rstd * (dv[j] * g[i][j] - c1 - xh * c2);
-        }
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (gy[i][j] - c1 - xh[i][j] * c2);
         if (HAS_RES) {
           float r[8];
           lds8(sbase + 2 * row_bytes + c * 16, r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = round_bf16(o[j]);
         store8(dx, DT_BF16, row * d + c * 8, o);
         if (want_cs) {
+          // column sums of dx (upstream bias gradient) from the fp32 values, before the bf16 rounding
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc_c[i][j] += o[j];
         }
@@ -339,7 +411,7 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < d; i += LN_THREADS) {
+  for (int i = threadIdx.x; i < d; i += LNP_THREADS) {
     if (dscale) atomicAdd(dscale + i, red[i]);
     if (dbias) atomicAdd(dbias + i, red[d + i]);
     if (want_cs) atomicAdd(dx_colsum + i, red[2 * d + i]);
@@ -352,8 +424,8 @@ int launch_ln_bwd_pipe(const void* dy, const void* x, const float* scale, const 
                        float* dx_colsum, int64_t rows, int d, cudaStream_t s) {
   const int narr = dres ? 3 : 2;
   const size_t smem = 3 * static_cast<size_t>(d) * 4 +
-                      static_cast<size_t>(LN_WARPS) * LNP_DEPTH * narr * d * 2;
-  int64_t blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+                      static_cast<size_t>(LNP_WARPS) * LNP_DEPTH * narr * d * 2;
+  int64_t blocks = (rows + LNP_WARPS - 1) / LNP_WARPS;
   const int64_t cap = num_sms();
   if (blocks > cap) blocks = cap;
   cudaError_t e;
@@ -361,14 +433,14 @@ int launch_ln_bwd_pipe(const void* dy, const void* x, const float* scale, const 
     auto k = ln_bwd_pipe_kernel<NCH, true>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_bwd_pipe)");
-    k<<<(unsigned)blocks, LN_THREADS, smem, s>>>(
+    k<<<(unsigned)blocks, LNP_THREADS, smem, s>>>(
         reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), scale, mean, rstd,
         reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dscale, dbias, dx_colsum, rows, d);
   } else {
     auto k = ln_bwd_pipe_kernel<NCH, false>;
     e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(ln_bwd_pipe)");
-    k<<<(unsigned)blocks, LN_THREADS, smem, s>>>(
+    k<<<(unsigned)blocks, LNP_THREADS, smem, s>>>(
         reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), scale, mean, rstd,
         nullptr, reinterpret_cast<bf16*>(dx), dscale, dbias, dx_colsum, rows, d);
   }
@@ -393,6 +465,18 @@ int launch_layernorm_fwd(const void* x, int x_dt, const float* scale, const floa
   if (rc) return rc;
   if (rows == 0) return BV_OK;
   const int nch = (d / 8 + 31) / 32;
+  if (x_dt == DT_BF16 && y_dt == DT_BF16 && rows >= 4096 && nch <= 3) {
+    // streaming fast path: two persistent blocks per SM
+    const unsigned pgrid = static_cast<unsigned>(2 * num_sms());
+    const bf16* xb = reinterpret_cast<const bf16*>(x);
+    bf16* yb = reinterpret_cast<bf16*>(y);
+    switch (nch) {
+      case 1: ln_fwd_stream_kernel<1><<<pgrid, LN_THREADS, 0, s>>>(xb, scale, bias, yb, mean, rstd, rows, d, eps); break;
+      case 2: ln_fwd_stream_kernel<2><<<pgrid, LN_THREADS, 0, s>>>(xb, scale, bias, yb, mean, rstd, rows, d, eps); break;
+      default: ln_fwd_stream_kernel<3><<<pgrid, LN_THREADS, 0, s>>>(xb, scale, bias, yb, mean, rstd, rows, d, eps); break;
+    }
+    return check_cuda(cudaGetLastError(), "ln_fwd_stream_kernel launch");
+  }
   const unsigned grid = static_cast<unsigned>((rows + LN_WARPS - 1) / LN_WARPS);
 #define LN_FWD_CASE(N)                                                                        \
   case N:                                                                                     \
@@ -420,14 +504,13 @@ int launch_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, con
     // streaming bf16 fast path (cp.async ring); the generic kernel below covers fp32 operands,
     // small problems and widths whose ring does not fit in shared memory
     const size_t ring = 3 * static_cast<size_t>(d) * 4 +
-                        static_cast<size_t>(LN_WARPS) * LNP_DEPTH * (dres ? 3 : 2) * d * 2;
-    if (dy_dt == DT_BF16 && x_dt == DT_BF16 && dx_dt == DT_BF16 && rows >= 4096 && nch <= 4 &&
+                        static_cast<size_t>(LNP_WARPS) * LNP_DEPTH * (dres ? 3 : 2) * d * 2;
+    if (dy_dt == DT_BF16 && x_dt == DT_BF16 && dx_dt == DT_BF16 && rows >= 4096 && nch <= 3 &&
         ring <= 220 * 1024) {
       switch (nch) {
         case 1: return launch_ln_bwd_pipe<1>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
         case 2: return launch_ln_bwd_pipe<2>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
-        case 3: return launch_ln_bwd_pipe<3>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
-        default: return launch_ln_bwd_pipe<4>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
+        default: return launch_ln_bwd_pipe<3>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
       }
     }
   }

@@ -95,7 +95,8 @@ def test_gemm_is_linear_at_full_size(ops):
   assert torch.equal(s1[rows], a1[rows].float() @ w.float())
 
 
-@pytest.mark.parametrize("rows,d", [(1000, 768), (77, 384), (513, 1024), (9, 64)])
+@pytest.mark.parametrize("rows,d", [(1000, 768), (77, 384), (513, 1024), (9, 64),
+                                    (5000, 768), (4099, 320), (4500, 1024)])   # >= 4096 rows: streaming kernels
 def test_layernorm(ops, rows, d):
   g = torch.Generator().manual_seed(rows)
   x = _bf(torch.randn(rows, d, generator=g) * 2 + 0.5)
@@ -117,7 +118,9 @@ def test_layernorm(ops, rows, d):
   _close(dx, xr.grad + dres.double(), 2 ** -7)
   _close(ds, sr.grad, 1e-4)
   _close(db, br.grad, 1e-4)
-  _close(cs, dx.double().sum(0), 1e-4)
+  # column sums of dx: the streaming kernel sums the fp32 values, the generic one the stored bf16
+  # values; both are within bf16 rounding noise (~2^-9 / 3) of the exact column sums
+  _close(cs, (xr.grad + dres.double()).sum(0), 3e-3)
 
 
 def test_layernorm_constant_rows_hit_the_variance_clamp(ops):
