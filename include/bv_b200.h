@@ -84,7 +84,8 @@ int bv_gemm(const bv_gemm_args* args, void* stream);
  * LayerNorm (flax nn.LayerNorm, eps=1e-6, fast variance; models/vit.py:92,103,160,181,
  * models/mlp_mixer.py:48,53,79).  x,y: [rows,d], d % 8 == 0, d <= 2048.
  * bwd: dx = dres + LN'(dy); dscale/dbias/dx_colsum are ACCUMULATED (atomics); any of
- * dres, dscale, dbias, dx_colsum may be NULL.  dres has dtype dx_dtype.
+ * dres, dscale, dbias, dx_colsum may be NULL.  dres has dtype dx_dtype.  dx_colsum receives the
+ * column sums of dx (summed in fp32; the streaming bf16 path sums before the bf16 rounding of dx).
  * --------------------------------------------------------------------------------- */
 int bv_layernorm_fwd(const void* x, int x_dtype, const float* scale, const float* bias, void* y,
                      int y_dtype, float* mean, float* rstd, int64_t rows, int32_t d, float eps,
