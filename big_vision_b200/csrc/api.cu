@@ -173,5 +173,14 @@ int bv_adam_step(const bv_adam_args* a, void* stream) {
 int bv_sumsq(const float* x, float* out, int64_t n, void* stream) {
   return launch_sumsq(x, out, n, S(stream));
 }
+int bv_top1(const void* logits, int logits_dtype, int64_t rows, int32_t C, int64_t ld, int32_t* idx,
+            const float* labels, int64_t ldl, const float* mask, float* top1_correct, float* sums,
+            void* stream) {
+  return launch_top1(logits, logits_dtype, rows, C, ld, idx, labels, ldl, mask, top1_correct, sums, S(stream));
+}
+int bv_retrieval_ranks(const float* dist, int64_t NI, int64_t NT, int64_t ld, const int32_t* corr,
+                       int32_t* rank_t2i, int32_t* rank_i2t, void* stream) {
+  return launch_retrieval_ranks(dist, NI, NT, ld, corr, rank_t2i, rank_i2t, S(stream));
+}
 
 }  // extern "C"

@@ -51,6 +51,13 @@ int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
 int gemm_debug_read(long long* host, int n);   // BV_GEMM_DBG=1 timeline of the last GEMM launch
 int attn_debug_read(long long* host, int n);   // BV_ATTN_DBG=1 timeline of the last fwd launch
 
+// ---- integer evaluation paths (eval.cu)
+int launch_top1(const void* logits, int dtype, int64_t rows, int C, int64_t ld, int32_t* idx,
+                const float* labels, int64_t ldl, const float* mask, float* top1_correct,
+                float* sums, cudaStream_t s);
+int launch_retrieval_ranks(const float* dist, int64_t NI, int64_t NT, int64_t ld, const int32_t* corr,
+                           int32_t* rank_t2i, int32_t* rank_i2t, cudaStream_t s);
+
 // ---- element-wise / reductions (elementwise.cu)
 int launch_patchify(const float* img, void* out, int64_t n, int H, int W, int C, int P,
                     cudaStream_t s);

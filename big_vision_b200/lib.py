@@ -80,6 +80,8 @@ SIGNATURES = {
     "bv_softmax_xent": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
     "bv_adam_step": [ctypes.POINTER(AdamArgs), c_vp],
     "bv_sumsq": [c_vp, c_vp, c_i64, c_vp],
+    "bv_top1": [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
+    "bv_retrieval_ranks": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp],
     "bv_version": [],
     "bv_device_supported": [],
 }
@@ -119,7 +121,7 @@ def check(rc, what):
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES = [0]
-_LAUNCHES_PER_CALL = {"bv_embed_bwd": 2}
+_LAUNCHES_PER_CALL = {"bv_embed_bwd": 2, "bv_retrieval_ranks": 2}
 
 
 # optional in-situ timing of every C-ABI call (bench.py --profile-calls): list of (name, e0, e1)

@@ -331,3 +331,39 @@ def adam_step(params, grads, mu, nu, params_bf16, *, lr_eff, b1, b2, eps, wd_eff
       upd_sq=upd_sq.data_ptr() if upd_sq is not None else None,
       param_sq=param_sq.data_ptr() if param_sq is not None else None)
   L.call("bv_adam_step", ctypes.byref(args), _stream())
+
+
+# ---- integer evaluation paths -------------------------------------------------------------------
+def top1(logits, labels=None, mask=None, want_idx=True):
+  """argmax over classes (+ label gather and masked counts).  Returns (idx int32 [rows] or None,
+  top1_correct fp32 [rows] or None, sums fp32 [2] = (ncorrect, nseen) or None)."""
+  if not logits.is_cuda:
+    raise L.BvError("bv_top1 needs CUDA tensors")
+  logits, ld = _rowmajor(logits)
+  rows, C = logits.shape
+  idx = torch.empty(rows, dtype=torch.int32, device=logits.device) if want_idx else None
+  correct = sums = None
+  ldl = 0
+  if labels is not None:
+    labels, ldl = _rowmajor(labels.float())
+    correct = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    sums = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    if mask is not None:
+      mask = mask.float().contiguous()
+  L.call("bv_top1", _p(logits), _dt(logits), rows, C, ld, _p(idx), _p(labels), ldl, _p(mask),
+         _p(correct), _p(sums), _stream())
+  return idx, correct, sums
+
+
+def retrieval_ranks(dist, corr, t2i=True, i2t=True):
+  """Positions of the positives in the ascending (stable) order of the columns / rows of the
+  distance matrix dist [NI, NT] fp32; corr int32 [NT].  Returns (rank_t2i [NT], rank_i2t [NI])."""
+  if not dist.is_cuda:
+    raise L.BvError("bv_retrieval_ranks needs CUDA tensors")
+  dist, ld = _rowmajor(dist)
+  NI, NT = dist.shape
+  corr = corr.to(device=dist.device, dtype=torch.int32).contiguous()
+  r_t2i = torch.empty(NT, dtype=torch.int32, device=dist.device) if t2i else None
+  r_i2t = torch.empty(NI, dtype=torch.int32, device=dist.device) if i2t else None
+  L.call("bv_retrieval_ranks", _p(dist), NI, NT, ld, _p(corr), _p(r_t2i), _p(r_i2t), _stream())
+  return r_t2i, r_i2t

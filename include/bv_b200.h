@@ -204,6 +204,26 @@ typedef struct bv_adam_args {
 int bv_adam_step(const bv_adam_args* args, void* stream);
 int bv_sumsq(const float* x, float* out, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Integer evaluation paths (bit-exact index arithmetic)
+ * bv_top1 -- evaluators/classification.py:46-52 and the zero-shot argmax of
+ *   evaluators/proj/image_text/discriminative_classifier.py:284-288:
+ *   idx[r] = argmax_c logits[r,c] (first maximal index, NaN counts as maximal; fp32 or bf16 logits,
+ *   row stride ld).  With labels [rows,C] fp32 (row stride ldl): top1_correct[r] = labels[r,idx[r]],
+ *   m[r] = mask[r] * max_c labels[r,c] (mask NULL = ones), sums[0] += sum top1_correct*m (ncorrect),
+ *   sums[1] += sum m (nseen).  idx, labels, mask, top1_correct, sums may each be NULL.
+ * bv_retrieval_ranks -- evaluators/proj/image_text/image_text_retrieval.py:23-85 on the distance
+ *   matrix dist [NI images, NT texts] fp32 (row stride ld) with corr[j] = image of text j:
+ *   rank_t2i[j] = position of image corr[j] in the ascending order of column j;
+ *   rank_i2t[i] = position of the first text of image i in the ascending order of row i
+ *   (INT32_MAX if image i has no text / corr[j] is out of range).  Ties order by index (stable
+ *   argsort).  Recall@k = mean(rank < k).  Either output may be NULL. */
+int bv_top1(const void* logits, int logits_dtype, int64_t rows, int32_t C, int64_t ld, int32_t* idx,
+            const float* labels, int64_t ldl, const float* mask, float* top1_correct, float* sums,
+            void* stream);
+int bv_retrieval_ranks(const float* dist, int64_t NI, int64_t NT, int64_t ld, const int32_t* corr,
+                       int32_t* rank_t2i, int32_t* rank_i2t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -311,3 +311,35 @@ def adam_reference(p, g, m, v, step, *, lr, b1, b2, eps, wd, sched=1.0, clip=0.0
   vhat = v / (1 - b2 ** step)
   upd = -sched * (lr * mhat / (np.sqrt(vhat) + eps) + wd * p)
   return p + upd, m, v
+
+
+# ----------------------------------------------------------------------------------------------
+# Integer evaluation paths (numpy; test infrastructure like the rest of this file)
+# ----------------------------------------------------------------------------------------------
+def top1_counts(logits, labels, mask=None):
+  """evaluators/classification.py:40-52: first-index argmax, label gather, masked counts."""
+  import numpy as np
+  logits = np.asarray(logits, np.float64)
+  labels = np.asarray(labels, np.float64)
+  mask = np.ones(len(logits)) if mask is None else np.asarray(mask, np.float64)
+  mask = mask * labels.max(axis=1)
+  idx = np.argmax(logits, axis=1)
+  correct = np.take_along_axis(labels, idx[:, None], axis=1)[:, 0]
+  return float((correct * mask).sum()), float(mask.sum()), idx.astype(np.int32)
+
+
+def retrieval_recalls(dist_matrix, corr, thresholds=(1, 5, 10)):
+  """evaluators/proj/image_text/image_text_retrieval.py:23-85 restated with a STABLE argsort
+  (the reference calls numpy's default argsort, whose tie order is unspecified for long arrays;
+  without ties the two are identical).  Returns (text->image dict, image->text dict)."""
+  import numpy as np
+  d = np.asarray(dist_matrix)
+  corr = np.asarray(corr)
+  per_text = d.argsort(axis=0, kind="stable")
+  per_image = d.argsort(axis=1, kind="stable")
+  t2i, i2t = {}, {}
+  for k in thresholds:
+    t2i[f"Recall@{k}"] = (per_text[:k, :] == corr[None]).any(axis=0).mean()
+    top_k = corr[per_image[:, :k]]
+    i2t[f"Recall@{k}"] = (top_k == np.arange(len(per_image))[:, None]).any(axis=1).mean()
+  return t2i, i2t
