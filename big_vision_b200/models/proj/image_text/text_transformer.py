@@ -123,3 +123,19 @@ class _Model:
 def Model(num_classes, *, variant=None, **kw):  # pylint: disable=invalid-name
   """Same factory as text_transformer.Model (text_transformer.py:102-105)."""
   return _Model(num_classes, **{**vit.decode_variant(variant), **kw})
+
+
+def load(init_params, init_file, model_cfg, dont_load=()):
+  """Init from a checkpoint -- models/proj/image_text/text_transformer.py:107-119 (including the
+  fix for old checkpoints that carried a second position embedding inside the encoder)."""
+  del model_cfg
+  from big_vision_b200 import utils
+  from big_vision_b200.models import common
+  params = dict(utils.load_params(init_file))
+  enc = dict(params["Encoder_0"])
+  extra_posemb = enc.pop("pos_embedding", 0)
+  params["Encoder_0"] = enc
+  params["pos_embedding"] = params["pos_embedding"] + extra_posemb
+  if "encoderblock" in enc:       # scan-stacked checkpoint into this (Python-loop) implementation
+    params = vit.scan_to_pyloop(params, encoder="Encoder_0")
+  return common.merge_params(params, init_params, dont_load)

@@ -85,3 +85,35 @@ class Model:
     if self.bias_init is not None:
       out["b"] = P.f("b")
     return zimg, ztxt, out
+
+
+def load(init_params, init_files, model_cfg, img_load_kw={}, txt_load_kw={}):  # pylint: disable=dangerous-default-value
+  """Loads both towers (+ t, b) -- models/proj/image_text/two_towers.py:92-135.  `init_files` is a
+  single two-tower .npz path or a dict with img / txt / t / b entries ('file.npz:subtree')."""
+  from big_vision_b200 import utils
+  if isinstance(init_files, str):
+    keys = ("img", "txt", "t", "b") if "bias_init" in model_cfg.keys() else ("img", "txt", "t")
+    init_files = {k: f"{init_files}:{k}" for k in keys}
+  else:
+    init_files = {**init_files}
+  if not init_params:
+    init_params = {"img": None, "txt": None}
+  restored = {**init_params}
+  img_init = init_files.pop("image", init_files.pop("img", None))
+  if img_init:
+    mod = importlib.import_module(f"big_vision_b200.models.{model_cfg.get('image_model', 'vit')}")
+    restored["img"] = mod.load(init_params["img"], img_init, model_cfg.get("image", {}), **img_load_kw)
+  txt_init = init_files.pop("text", init_files.pop("txt", None))
+  if txt_init:
+    mod = importlib.import_module(
+        f"big_vision_b200.models.{model_cfg.get('text_model', 'proj.image_text.text_transformer')}")
+    restored["txt"] = mod.load(init_params["txt"], txt_init, model_cfg.get("text", {}), **txt_load_kw)
+  t_init = init_files.pop("temperature", init_files.pop("t", None))
+  if t_init:
+    restored["t"] = utils.load_params(t_init)
+  b_init = init_files.pop("bias", init_files.pop("b", None))
+  if b_init:
+    restored["b"] = utils.load_params(b_init)
+  assert not init_files, (f"There's something unused left in `config.model_init`. You probably got "
+                          f"a typo. Here it is: {init_files}")
+  return restored

@@ -491,3 +491,94 @@ class _Model:
 def Model(num_classes=None, *, variant=None, **kw):  # pylint: disable=invalid-name
   """Factory, same signature as big_vision.models.vit.Model (models/vit.py:279-281)."""
   return _Model(num_classes, **{**decode_variant(variant), **kw})
+
+
+# ----------------------------------------------------------------------------------------------
+# Checkpoint loading (host side; nested dicts of numpy arrays under the reference's names).
+# Mirrors models/vit.py:306-433.
+# ----------------------------------------------------------------------------------------------
+def resample_posemb(old, new):
+  """'High-res finetuning': bilinear (order-1 spline) rescale of the [1, N, d] grid of position
+  embeddings to the shape of `new` -- models/vit.py:306-322."""
+  import scipy.ndimage
+  old = np.asarray(old)
+  if old.shape == tuple(new.shape):
+    return old
+  gs_old = int(np.sqrt(old.shape[1]))
+  gs_new = int(np.sqrt(new.shape[1]))
+  grid = old.reshape(gs_old, gs_old, -1)
+  zoom = (gs_new / gs_old, gs_new / gs_old, 1)
+  grid = scipy.ndimage.zoom(grid, zoom, order=1)
+  return grid.reshape(1, gs_new * gs_new, -1)
+
+
+def fix_old_checkpoints(params):
+  """Small backward incompatibilities of old ViT checkpoints -- models/vit.py:325-365 (the
+  pre-linen conversion of the reference is not applicable to .npz trees written by linen code)."""
+  params = {k: (dict(v) if isinstance(v, dict) else v) for k, v in params.items()}
+  t = params.get("Transformer", {})
+  if "posembed_input" in t:                       # original ViT paper variant: posemb in a module
+    params["pos_embedding"] = t.pop("posembed_input")["pos_embedding"]
+  if "pos_embedding" in t:                        # pre-2022: posemb inside the Encoder
+    params["pos_embedding"] = t.pop("pos_embedding")
+  if "pos_embedding" in params:                   # old: [cls] concatenated before adding posemb
+    pe = params["pos_embedding"]
+    if int(np.sqrt(pe.shape[1])) ** 2 + 1 == int(pe.shape[1]):
+      pe_cls, params["pos_embedding"] = pe[:, :1], pe[:, 1:]
+      if "cls" in params:
+        params["cls"] = params["cls"] + pe_cls
+  if "probe" in params:                           # MAP head inlined during ViT-G development
+    params["MAPHead_0"] = {k: params.pop(k) for k in
+                           ["probe", "MlpBlock_0", "MultiHeadDotProductAttention_0", "LayerNorm_0"]}
+  return params
+
+
+def _map_leaves(fn, *trees):
+  if isinstance(trees[0], dict):
+    return {k: _map_leaves(fn, *[t[k] for t in trees]) for k in trees[0]}
+  return fn(*trees)
+
+
+def pyloop_to_scan(params_pyloop, encoder="Transformer"):
+  """encoderblock_{i} sub-trees -> one 'encoderblock' with a leading depth axis -- vit.py:368-390."""
+  params = dict(params_pyloop)
+  t = dict(params[encoder])
+  blocks = {k for k in t if k.startswith("encoderblock_")}
+  depth = 1 + max(int(k.split("_")[-1]) for k in blocks)
+  t["encoderblock"] = _map_leaves(lambda *v: np.stack(v), *[t[f"encoderblock_{i}"] for i in range(depth)])
+  for i in range(depth):
+    del t[f"encoderblock_{i}"]
+  params[encoder] = t
+  return params
+
+
+def scan_to_pyloop(params_scan, encoder="Transformer"):
+  """The inverse of pyloop_to_scan -- vit.py:393-409."""
+  params = dict(params_scan)
+  t = dict(params[encoder])
+  depth = len(t["encoderblock"]["LayerNorm_0"]["bias"])
+  for i in range(depth):
+    t[f"encoderblock_{i}"] = _map_leaves(lambda x, i=i: x[i], t["encoderblock"])
+  del t["encoderblock"]
+  params[encoder] = t
+  return params
+
+
+def load(init_params, init_file, model_cfg, dont_load=()):
+  """Init from a checkpoint, old formats included, + hi-res posemb -- models/vit.py:412-433.
+  `init_params` / the result are nested dicts under the reference names (use
+  `utils.recover_tree(*zip(*P.numpy_tree().items()))` and `P.load_tree(dict(flatten))` to go from
+  and to a FlatParams).  This implementation runs the blocks as a Python loop (`scan=False`)."""
+  from big_vision_b200 import utils
+  from big_vision_b200.models import common
+  restored = utils.load_params(init_file)
+  restored = fix_old_checkpoints(restored)
+  if model_cfg.get("scan") and "encoderblock" not in restored["Transformer"]:
+    restored = pyloop_to_scan(restored)
+  if not model_cfg.get("scan") and "encoderblock" in restored["Transformer"]:
+    restored = scan_to_pyloop(restored)
+  restored = common.merge_params(restored, init_params, dont_load)
+  if init_params and "pos_embedding" in init_params:
+    restored["pos_embedding"] = resample_posemb(old=restored["pos_embedding"],
+                                                new=init_params["pos_embedding"])
+  return restored

@@ -81,3 +81,136 @@ def create_learning_rate_schedule(total_steps, batch_size=None, data_size=None, 
     return float(np.float32(lr))
 
   return step_fn
+
+
+# ----------------------------------------------------------------------------------------------
+# Checkpoint interchange: the reference's .npz format (flat "a/b/c" keys), SURVEY 8f rank 3.
+# Trees are nested dicts (tuples / lists by index) of numpy arrays; everything here is host code.
+# ----------------------------------------------------------------------------------------------
+import collections as _collections
+import os as _os
+import re as _re
+
+
+def _traverse_with_names(tree, with_inner_nodes=False):
+  """(name, leaf) pairs in sorted-key order -- utils.py:616-640."""
+  if tree is None:
+    return
+  if isinstance(tree, dict):
+    for key in sorted(tree.keys()):
+      for path, v in _traverse_with_names(tree[key], with_inner_nodes):
+        yield (key + "/" + path).rstrip("/"), v
+    if with_inner_nodes:
+      yield "", tree
+  elif isinstance(tree, (list, tuple)):
+    for idx in range(len(tree)):
+      for path, v in _traverse_with_names(tree[idx], with_inner_nodes):
+        yield (str(idx) + "/" + path).rstrip("/"), v
+    if with_inner_nodes:
+      yield "", tree
+  else:
+    yield "", tree
+
+
+def tree_flatten_with_names(tree):
+  """[(name, value), ...] -- utils.py:642-670 for dict / tuple / list trees (for those, jax's
+  flattening order is the sorted-key order produced here).  Returns (names_and_vals, None)."""
+  return list(_traverse_with_names(tree)), None
+
+
+def tree_get(tree, name):
+  """Entry of a tree by flattened key, e.g. 'a/b/c' or an inner node 'a/b' -- utils.py:726-752."""
+  flattened = dict(_traverse_with_names(tree, with_inner_nodes=True))
+  try:
+    return flattened[name]
+  except KeyError:
+    raise KeyError("\n".join([name, "Available keys:", *flattened, ""])) from None
+
+
+def recover_tree(keys, values):
+  """Nested dict from flat '/'-separated names -- utils.py:836-862."""
+  tree = {}
+  sub_trees = _collections.defaultdict(list)
+  for k, v in zip(keys, values):
+    if "/" not in k:
+      tree[k] = v
+    else:
+      k_left, k_right = k.split("/", 1)
+      sub_trees[k_left].append((k_right, v))
+  for k, kv_pairs in sub_trees.items():
+    k_subtree, v_subtree = zip(*kv_pairs)
+    tree[k] = recover_tree(k_subtree, v_subtree)
+  return tree
+
+
+def recover_dtype(a):
+  """numpy stores bfloat16 as a 2-byte void type (utils.py:827-833); there is no numpy bfloat16
+  here, so such arrays come back as float32 (exact: bf16 is the top half of fp32)."""
+  if hasattr(a, "dtype") and a.dtype.type is np.void:
+    assert a.itemsize == 2, "Unknown dtype!"
+    return (a.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+  return a
+
+
+def npload(fname):
+  """np.ndarray (np.save file) or dict of arrays (np.savez file) -- utils.py:133-149."""
+  loaded = np.load(fname, allow_pickle=False)
+  return loaded if isinstance(loaded, np.ndarray) else dict(loaded)
+
+
+def load_checkpoint_np(npz):
+  """Nested tree from a .npz path or dict-like of flat names -- utils.py:152-170."""
+  if isinstance(npz, str):
+    npz = npload(npz)
+  keys, values = zip(*list(npz.items()))
+  return recover_tree(keys, values)
+
+
+def _tree_map(fn, tree):
+  if isinstance(tree, dict):
+    return {k: _tree_map(fn, v) for k, v in tree.items()}
+  if isinstance(tree, (list, tuple)):
+    return type(tree)(_tree_map(fn, v) for v in tree)
+  return fn(tree)
+
+
+def load_params(ckpt):
+  """Parameters of a big_vision .npz checkpoint -- utils.py:173-228 (npz branch).  `ckpt` may be
+  '/path/file.npz:img/head' to take a sub-tree, or an already-loaded dict-like.  Handles the three
+  containers the reference does: {'params': ...}, {'opt': {'target': ...}}, or the bare tree."""
+  key = None
+  if isinstance(ckpt, str):
+    match = _re.match(r"^(.*?/.*?)(?::([\w/]+))?$", ckpt)
+    if not match:
+      raise ValueError(f"Weird ckpt path: {ckpt} ; Maybe prepend ./ ?")
+    ckpt, key = match.groups()
+    if ".npz" not in ckpt:
+      raise ValueError("only the .npz checkpoint format is supported here")
+  checkpoint = _tree_map(recover_dtype, load_checkpoint_np(ckpt))
+  if "params" in checkpoint:
+    params = checkpoint["params"]
+  elif "opt" in checkpoint:
+    params = checkpoint["opt"]["target"]
+  else:
+    params = checkpoint
+  if key is not None:
+    params = tree_get(params, key)
+  return params
+
+
+def save_checkpoint_np(checkpoint, path):
+  """Writes a tree as the reference's .npz: one array per leaf under its flat name, atomically
+  (temporary file + rename), like the reference's npz writer."""
+  names_and_vals, _ = tree_flatten_with_names(checkpoint)
+  tmp = path + "-TEMPORARY.npz"
+  with open(tmp, "wb") as f:
+    np.savez(f, **{k: np.asarray(v) for k, v in names_and_vals})
+  _os.replace(tmp, path)
+
+
+def check_and_compile_patterns(patterns):
+  """utils.py: a str or a sequence of regex strs -> compiled patterns."""
+  if isinstance(patterns, str):
+    patterns = [patterns]
+  assert isinstance(patterns, (list, tuple)), patterns
+  return [_re.compile(p) for p in patterns]
