@@ -126,6 +126,9 @@ int bv_tanh_bwd(const void* dy, const void* y, void* dx, int dtype, int64_t n, v
 int bv_gelu_fwd(const void* x, void* y, int dtype, int64_t n, void* stream) {
   return launch_gelu_fwd(x, y, dtype, n, S(stream));
 }
+int bv_mixup(const float* x, float* out, int64_t n, int64_t row_elems, float a, void* stream) {
+  return launch_mixup(x, out, n, row_elems, a, S(stream));
+}
 int bv_axpby(const void* x, const void* y, void* out, int dtype, float a, float b, int64_t n,
              void* stream) {
   return launch_axpby(x, y, out, dtype, a, b, n, S(stream));

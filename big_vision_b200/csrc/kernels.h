@@ -87,6 +87,7 @@ int launch_add_rows(const void* x, int x_dtype, const float* row, void* y, int y
 int launch_tanh_fwd(const void* x, void* y, int dtype, int64_t n, cudaStream_t s);
 int launch_tanh_bwd(const void* dy, const void* y, void* dx, int dtype, int64_t n, cudaStream_t s);
 int launch_gelu_fwd(const void* x, void* y, int dtype, int64_t n, cudaStream_t s);
+int launch_mixup(const float* x, float* out, int64_t n, int64_t row_elems, float a, cudaStream_t s);
 int launch_axpby(const void* x, const void* y, void* out, int dtype, float a, float b, int64_t n,
                  cudaStream_t s);
 int launch_transpose_tokens(const void* x, void* y, int64_t n, int N, int d, cudaStream_t s);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "bv_tanh_fwd": [c_vp, c_vp, c_i32, c_i64, c_vp],
     "bv_tanh_bwd": [c_vp, c_vp, c_vp, c_i32, c_i64, c_vp],
     "bv_gelu_fwd": [c_vp, c_vp, c_i32, c_i64, c_vp],
+    "bv_mixup": [c_vp, c_vp, c_i64, c_i64, c_f32, c_vp],
     "bv_axpby": [c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp],
     "bv_transpose_tokens": [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "bv_untranspose_add": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],

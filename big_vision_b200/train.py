@@ -3,8 +3,8 @@
   logits = model(images) ; loss = getattr(u, config.loss)(logits, labels) (mean over batch)
   grads  = d loss / d params ; data-parallel mean over ranks ; fused Adam step.
 
-Mixup (train.py:283-290, utils.py:1146-1154) is not built yet (SURVEY 8f "next" #4); a config that
-asks for it raises.  Losses: sigmoid_xent / softmax_xent (utils.py:236-243, 276-281) as fused
+Mixup (train.py:283-290, utils.py:1146-1158) runs per rank on that rank's shard, as the reference's
+shard_map does.  Losses: sigmoid_xent / softmax_xent (utils.py:236-243, 276-281) as fused
 loss+gradient kernels.
 """
 import torch
@@ -29,15 +29,19 @@ def loss_and_grads(model, P, images, labels, loss_name="sigmoid_xent"):
 
 
 def make_update_fn(model, tx, config):
-  if config.get("mixup") and config["mixup"].get("p"):
-    raise NotImplementedError("mixup is not built on this path yet")
+  mixup_p = (config.get("mixup") or {}).get("p")
   loss_name = config.get("loss", "sigmoid_xent")
   d = Dist()
 
   def update_fn(train_state, rng, batch):
-    del rng
     P, opt = train_state["params"], train_state["opt"]
-    loss, _ = loss_and_grads(model, P, batch["image"], batch["labels"], loss_name)
+    images, labels = batch["image"], batch["labels"]
+    if mixup_p:
+      from big_vision_b200 import utils as u
+      if rng is None:
+        raise ValueError("mixup needs an rng (numpy Generator)")
+      rng, (images, labels), _ = u.get_mixup(rng, mixup_p)(images, labels)
+    loss, _ = loss_and_grads(model, P, images, labels, loss_name)
     # the loss is the mean over the GLOBAL batch: sum the per-rank means and divide by world
     d.all_reduce_sum(P.grad)
     d.all_reduce_sum(loss)

@@ -214,3 +214,27 @@ def check_and_compile_patterns(patterns):
     patterns = [patterns]
   assert isinstance(patterns, (list, tuple)), patterns
   return [_re.compile(p) for p in patterns]
+
+
+# ----------------------------------------------------------------------------------------------
+# mixup (utils.py:1146-1158)
+# ----------------------------------------------------------------------------------------------
+def get_mixup(rng, p):
+  """Mirror of `get_mixup(rng, p)`: draws a ~ Beta(p, p), a = max(a, 1 - a), and returns
+  `_mixup(*things, **more_things) -> (rng, things, more_things)` mixing every thing with its roll
+  by one along the batch axis (`bv_mixup`).  `rng` is a numpy Generator (the reference's is a jax
+  PRNG key; the stream of random numbers is necessarily a different one, the arithmetic is not)."""
+  a = float(rng.beta(p, p))
+  a = max(a, 1.0 - a)
+
+  def _mixup(*things, **more_things):
+    from big_vision_b200 import ops
+    mix = lambda thing: ops.mixup(thing, a)
+    return rng, tuple(mix(t) for t in things), {k: mix(v) for k, v in more_things.items()}
+
+  _mixup.a = a
+  return _mixup
+
+
+def mixup(rng, *things, p, **more_things):
+  return get_mixup(rng, p)(*things, **more_things)

@@ -154,6 +154,9 @@ int bv_broadcast_row(const void* x, int x_dtype, const float* row, void* y, int 
 int bv_tanh_fwd(const void* x, void* y, int dtype, int64_t n, void* stream);
 int bv_tanh_bwd(const void* dy, const void* y, void* dx, int dtype, int64_t n, void* stream);
 int bv_gelu_fwd(const void* x, void* y, int dtype, int64_t n, void* stream);
+/* utils.py:1146-1158 (get_mixup): out[i,:] = a * x[i,:] + (1-a) * x[(i-1) mod n,:], fp32, out != x;
+ * products and sum rounded separately (bit-identical to the fp32 expression). row_elems % 4 == 0. */
+int bv_mixup(const float* x, float* out, int64_t n, int64_t row_elems, float a, void* stream);
 int bv_axpby(const void* x, const void* y, void* out, int dtype, float a, float b, int64_t n,
              void* stream);
 /* cls token (models/vit.py:223-225): out[b,0,:] = cls, out[b,1+t,:] = x[b,t,:]  (bf16, cls fp32) */

@@ -95,3 +95,47 @@ def test_classifier_update_fn_runs_and_learns():
     state, m = fn(state, None, batch)
     losses.append(float(m["training_loss"]))
   assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("shape,a", [((8, 64, 64, 3), 0.73), ((5, 1000), 0.5), ((1, 8), 0.9), ((3, 4), 1.0)])
+def test_mixup_kernel_is_bit_exact(shape, a):
+  """utils.py:1146-1158: a*x + (1-a)*roll(x, 1, axis=0), evaluated in fp32 with each product and
+  the sum rounded separately -- identical bits to the numpy fp32 expression."""
+  from big_vision_b200 import ops
+  x = np.random.default_rng(7).standard_normal(shape).astype(np.float32)
+  a32 = np.float32(a)
+  ref = a32 * x + (np.float32(1) - a32) * np.roll(x, 1, axis=0)
+  assert ref.dtype == np.float32
+  got = ops.mixup(torch.from_numpy(x).cuda(), float(a32)).cpu().numpy()
+  assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_update_fn_with_mixup_equals_step_on_mixed_batch():
+  """The trainer draws a ~ Beta(p,p), a = max(a, 1-a), and mixes images and labels of this rank's
+  shard before the step: its loss equals loss_and_grads on the host-mixed batch with the same a."""
+  from big_vision_b200 import optax as bv_optax, train, utils as u
+  from big_vision_b200.models import vit
+  model = vit.Model(16, width=64, depth=2, mlp_dim=128, num_heads=1, patch_size=(16, 16),
+                    pool_type="gap", rep_size=False)
+  P = model.init(0, (8, 64, 64, 3), device="cuda")
+  P.load_tree(_randomize_zero_inits(P.numpy_tree("f"), 1))
+  config = dict(optax_name="scale_by_adam", optax=dict(mu_dtype="float32"), lr=0.0, wd=0.0,
+                loss="softmax_xent", mixup=dict(p=0.2), schedule=dict(decay_type="cosine", warmup_steps=0))
+  tx, _ = bv_optax.make(config, P, sched_kw=dict(total_steps=100, batch_size=8, data_size=1000))
+  state = {"params": P, "opt": tx.init(P)}
+  fn = train.make_update_fn(model, tx, config)
+  rng = np.random.default_rng(3)
+  image = rng.uniform(-1, 1, (8, 64, 64, 3)).astype(np.float32)
+  labels = np.eye(16, dtype=np.float32)[rng.integers(0, 16, 8)]
+  a = u.get_mixup(np.random.default_rng(11), 0.2).a
+  assert 0.5 <= a <= 1.0
+  a32 = np.float32(a)
+  mix = lambda t: a32 * t + (np.float32(1) - a32) * np.roll(t, 1, axis=0)
+  ref_loss, _ = train.loss_and_grads(model, P, torch.from_numpy(mix(image)).cuda(),
+                                     torch.from_numpy(mix(labels)).cuda(), "softmax_xent")
+  ref_loss = float(ref_loss)
+  with pytest.raises(ValueError):
+    fn(state, None, {"image": torch.from_numpy(image).cuda(), "labels": torch.from_numpy(labels).cuda()})
+  state, m = fn(state, np.random.default_rng(11), {"image": torch.from_numpy(image).cuda(),
+                                                    "labels": torch.from_numpy(labels).cuda()})
+  assert float(m["training_loss"]) == ref_loss

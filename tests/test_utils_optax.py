@@ -51,3 +51,14 @@ def test_make_rejects_unbuilt_configurations():
                                grad_clip_norm=1.0, schedule=dict(decay_type="cosine", warmup_steps=2)),
                           None, sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
   assert tx.b2 == 0.95 and tx.clip == 1.0 and fns[0](0) == 0.0 and fns[0](2) == pytest.approx(1.0)
+
+
+def test_get_mixup_draws_a_at_least_one_half():
+  """utils.py:1146-1150: a ~ Beta(p, p) then a = max(a, 1 - a)."""
+  import numpy as np
+  from big_vision_b200 import utils as u
+  for seed in range(20):
+    a = u.get_mixup(np.random.default_rng(seed), 0.2).a
+    assert 0.5 <= a <= 1.0
+    b = np.random.default_rng(seed).beta(0.2, 0.2)
+    assert a == max(b, 1.0 - b)
