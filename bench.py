@@ -29,6 +29,8 @@ OPT_CONFIG = dict(optax_name="scale_by_adam", optax=dict(b2=0.95, mu_dtype="bflo
 RES, TXT_LEN = 224, 64
 # algorithmic training FLOPs per image-text pair (3 x forward; SURVEY.md 8d / BASELINE.md 3)
 FLOPS_PER_PAIR = 139.3e9
+WORKLOAD = ("SigLIP two_towers ViT-B/16 (map pool) + text-B (64 tok, vocab 32000), 224x224, full update_fn "
+            "(fwd, sigmoid loss over gathered ztxt, bwd, grad all-reduce, Adam)")
 # ncu-measured DRAM traffic per GEMM launch (all GEMM launches of one bench run, see profiles/)
 NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 0.927e9
 
@@ -135,25 +137,57 @@ def cpu_port_step(pairs, threads=None):
   return time.perf_counter() - t0
 
 
+def usable_host_threads():
+  """Threads the CPU legs may use: torch's default intra-op pool, capped by the scheduler affinity
+  and the cgroup CPU quota.  More threads than runnable CPUs makes the OpenMP barriers of these
+  small-batch ops spin against each other (observed: minutes per step instead of seconds)."""
+  import math
+  import torch
+  n = torch.get_num_threads()
+  try:
+    n = min(n, len(os.sched_getaffinity(0)))
+  except AttributeError:
+    pass
+  try:
+    quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+    if quota != "max":
+      n = min(n, max(1, math.ceil(int(quota) / int(period))))
+  except (OSError, ValueError):
+    pass
+  return max(1, n)
+
+
 def run_reference(args):
   import torch
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
-  threads = os.cpu_count() or 1
-  pairs = 8
-  for _ in range(max(1, min(args.warmup, 1))):
+  threads = usable_host_threads()
+  # Each step is a bounded sample of the workload: `pairs` image-text pairs through fwd + bwd of the
+  # oracle port.  K and W are honoured; the sample shrinks (8 -> 4 -> 2 -> 1 pairs) if the first
+  # step shows that W + K steps would not finish within ~3 minutes on this host.
+  pairs, budget_s = 8, 180.0
+  warmup = max(1, args.warmup)
+  steps = max(1, args.steps)
+  t_first = cpu_port_step(pairs, threads)          # warm-up step 1 (allocations, MKL plans)
+  est = t_first * (warmup - 1 + steps)
+  while est > budget_s and pairs > 1:
+    pairs //= 2
+    est /= 2
+  if est > budget_s:                               # pathological host: keep the run bounded anyway
+    steps = max(1, int(budget_s / (est / (warmup - 1 + steps))) - (warmup - 1))
+  for _ in range(warmup - 1):
     cpu_port_step(pairs, threads)
-  steps = max(1, min(args.steps, 4))
   t = sum(cpu_port_step(pairs, threads) for _ in range(steps))
   val = pairs * steps / t
   line = {
       "impl": "reference", "metric": "siglip_vit_b16_pairs_per_sec", "value": val, "unit": "pairs/s",
-      "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * t / steps,
+      "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t / steps,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
       "data": "synthetic",
-      "config": {"workload": "SigLIP two_towers ViT-B/16 img + B txt (64 tok), fwd+bwd of the pairwise "
-                             "sigmoid loss, 224x224", "global_batch": pairs, "parallelism": "cpu"},
+      "config": {"workload": WORKLOAD, "global_batch": pairs, "parallelism": f"cpu{threads}",
+                 "sample": "fwd+bwd of the pairwise sigmoid loss through both towers on a bounded "
+                           "sample of the batch (no optimizer step)"},
       "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
                        "sample": f"{steps} steps x {pairs} pairs, oracle port (torch-CPU fp32, no optimizer)"},
       "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -330,9 +364,11 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
       steps_cpu, pairs_cpu = 2, 8
-      cpu_port_step(pairs_cpu)
-      tt = sum(cpu_port_step(pairs_cpu) for _ in range(steps_cpu))
-      cpu = {"value": pairs_cpu * steps_cpu / tt, "unit": "pairs/s", "cores": torch.get_num_threads(),
+      nthr = usable_host_threads()
+      t_warm = cpu_port_step(pairs_cpu, nthr)
+      steps_cpu = max(1, min(steps_cpu, int(60.0 / max(t_warm, 1e-3))))
+      tt = sum(cpu_port_step(pairs_cpu, nthr) for _ in range(steps_cpu))
+      cpu = {"value": pairs_cpu * steps_cpu / tt, "unit": "pairs/s", "cores": nthr,
              "kind": "port", "sample": f"{steps_cpu} steps x {pairs_cpu} pairs fwd+bwd, oracle port in "
                                        "torch-CPU fp32 (no optimizer step)"}
     line = {
@@ -340,9 +376,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "SigLIP two_towers ViT-B/16 (map pool) + text-B (64 tok, vocab 32000), "
-                               "224x224, full update_fn (fwd, sigmoid loss over gathered ztxt, bwd, "
-                               "grad all-reduce, Adam)",
+        "config": {"workload": WORKLOAD,
                    "global_batch": n * world, "per_gpu_batch": n, "seq_len": 196 + TXT_LEN,
                    "parallelism": f"dp{world}", "l2_policy": "inputs (616 MB images/step) and "
                    "activations (>70 GB) exceed the 126 MB L2; no explicit flush",
