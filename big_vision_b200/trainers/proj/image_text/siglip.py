@@ -44,6 +44,21 @@ class Dist:
                 lambda: dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM))
     return out
 
+  def broadcast_rows(self, x, src):
+    """Every rank receives rank `src`'s x (same shape on all ranks)."""
+    if self.world == 1:
+      return x
+    buf = x.contiguous().clone() if self.rank == src else torch.empty_like(x)
+    self._timed("nccl_broadcast", lambda: dist.broadcast(buf, src=src))
+    return buf
+
+  def reduce_rows(self, x, dst):
+    """Sum over ranks delivered to rank `dst` (the other ranks' return value is scratch)."""
+    if self.world > 1:
+      x = x.contiguous()
+      self._timed("nccl_reduce", lambda: dist.reduce(x, dst=dst, op=dist.ReduceOp.SUM))
+    return x
+
   def all_reduce_sum(self, x):
     if self.world > 1:
       self._timed("nccl_all_reduce", lambda: dist.all_reduce(x, op=dist.ReduceOp.SUM))
@@ -86,11 +101,51 @@ def sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal):
   return dzimg, dztxt
 
 
+def chunked_sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal):
+  """The memory-lean variant of the same loss: section 3.1 of arxiv.org/abs/2303.15343,
+  `chunked_sigmoid_loss` in _deprecated_contrastive.py:168-200.  G rounds; round r scores the local
+  images against rank r's texts only, so the live slab is [n, n] instead of [n, B].  Positives sit
+  on the diagonal of the round r == rank; every other round is all negatives (row_offset = -n puts
+  the positive column outside the block).  The reference gathers the chunk with a masked psum;
+  here it is a broadcast from its owner, and the chunk's gradient is reduced back to the owner.
+  Same arguments and return values as sigmoid_loss_fwd_bwd; same loss value and gradients."""
+  n, D = zimg.shape
+  B = n * d.world
+  zi16 = ops.cast(zimg, torch.empty_like(zimg, dtype=torch.bfloat16))
+  has_b = "b" in P.offsets
+  dzimg = torch.zeros((n, D), dtype=torch.float32, device=zimg.device)
+  dztxt = None
+  for r in range(d.world):
+    chunk = d.broadcast_rows(ztxt, src=r)                          # C1, one peer per round
+    zc16 = ops.cast(chunk, torch.empty_like(chunk, dtype=torch.bfloat16))
+    dots = ops.gemm(zi16, zc16, out_dtype=torch.float32)           # [n, n]
+    G = ops.siglip_loss(dots, 0 if r == d.rank else -n, P.f("t"), P.f("b") if has_b else None, B,
+                        scal[0:1], P.g("t"), P.g("b") if has_b else None)
+    ops.gemm(G, zc16, b_mn=True, out=dzimg, reduce_out=True)       # dzimg += G . chunk
+    dzc = ops.gemm(G, zi16, a_mn=True, b_mn=True, out_dtype=torch.float32)   # G^T . zimg  [n, D]
+    dzc = d.reduce_rows(dzc, dst=r)                                # C2, delivered to the owner
+    if r == d.rank:
+      dztxt = dzc
+  return dzimg, dztxt
+
+
+_LOSS_FNS = {"sigmoid": sigmoid_loss_fwd_bwd, "chunked_sigmoid": chunked_sigmoid_loss_fwd_bwd}
+
+
+def _loss_fn(config):
+  """config.loss_fn as in _deprecated_contrastive.py:322-331 ('sigmoid' is what siglip.py runs)."""
+  name = (config or {}).get("loss_fn", "sigmoid")
+  if name not in _LOSS_FNS:
+    raise NotImplementedError(f"Unrecognized loss config.loss_fn={name!r} (built: {sorted(_LOSS_FNS)})")
+  return _LOSS_FNS[name]
+
+
 def make_update_fn(model, tx, config=None):
   """Returns update_fn(train_state, rng, batch) -> (train_state, measurements), the
   signature of siglip.py:275.  train_state = {"params": FlatParams, "opt": opt_state};
   it is updated IN PLACE (the reference donates it, siglip.py:273)."""
   d = Dist()
+  loss_fwd_bwd = _loss_fn(config)
 
   def update_fn(train_state, rng, batch):
     del rng  # dropout is 0 on this path; nothing stochastic in the step
@@ -99,7 +154,7 @@ def make_update_fn(model, tx, config=None):
     P.zero_grad()
     scal = torch.zeros(4, dtype=torch.float32, device=P.flat.device)
     zimg, ztxt, saved = model.fwd(P, images, labels)
-    dzimg, dztxt = sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal)
+    dzimg, dztxt = loss_fwd_bwd(P, zimg, ztxt, d, scal)
     model.bwd(P, dzimg, dztxt, saved)
     d.all_reduce_sum(P.grad)                               # C3 (+ dt, db inside the flat buffer)
     d.all_reduce_sum(scal)                                 # C4: loss
@@ -115,10 +170,11 @@ def make_update_fn(model, tx, config=None):
   return update_fn
 
 
-def loss_and_grads(model, P, images, labels):
+def loss_and_grads(model, P, images, labels, loss_fn="sigmoid"):
   """value_and_grad(loss_fn)(params) of siglip.py:287-311 without the optimizer: returns the
   global loss (device scalar) with P.grad holding d loss / d params (summed over ranks)."""
   d = Dist()
+  sigmoid_loss_fwd_bwd = _loss_fn({"loss_fn": loss_fn})   # pylint: disable=redefined-outer-name
   P.zero_grad()
   scal = torch.zeros(4, dtype=torch.float32, device=P.flat.device)
   zimg, ztxt, saved = model.fwd(P, images, labels)

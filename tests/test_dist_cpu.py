@@ -18,7 +18,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, loss_fn="sigmoid"):
   sys.path.insert(0, ROOT)
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
   dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -30,10 +30,17 @@ def _worker(rank, world, port, ret):
   def cast(src, dst):
     return src          # keep fp32: this test is about the sharding algebra, not bf16 rounding
 
-  def gemm(a, b, a_mn=False, b_mn=False, out_dtype=torch.float32, **kw):
+  def gemm(a, b, a_mn=False, b_mn=False, out_dtype=torch.float32, out=None, reduce_out=False, **kw):
     A = a.double().T if a_mn else a.double()
     Bm = b.double() if b_mn else b.double().T
-    return (A @ Bm).to(out_dtype)
+    res = A @ Bm
+    if out is None:
+      return res.to(out_dtype)
+    if reduce_out:
+      out += res.to(out.dtype)
+    else:
+      out.copy_(res.to(out.dtype))
+    return out
 
   def siglip_loss(dots, row_offset, t_param, b_param, global_b, loss, dt, db):
     d = dots.double().requires_grad_(True)
@@ -41,7 +48,9 @@ def _worker(rank, world, port, ret):
     b = b_param.double().requires_grad_(True)
     n, B = d.shape
     m = -torch.ones(n, B, dtype=torch.float64)
-    m[torch.arange(n), row_offset + torch.arange(n)] = 1
+    cols = row_offset + torch.arange(n)
+    ok = (cols >= 0) & (cols < B)                 # a block without this rank's positives: none
+    m[torch.arange(n)[ok], cols[ok]] = 1
     l = -(torch.nn.functional.logsigmoid(m * (d * t.exp() + b))).sum() / global_b
     l.backward()
     loss += l.detach().float()
@@ -65,8 +74,9 @@ def _worker(rank, world, port, ret):
   zt = O.l2_normalize(torch.randn(B, D, generator=g).double())
   P = FakeP()
   scal = torch.zeros(4)
-  dzimg, dztxt = siglip.sigmoid_loss_fwd_bwd(P, zi[rank * n:(rank + 1) * n].float(),
-                                             zt[rank * n:(rank + 1) * n].float(), siglip.Dist(), scal)
+  fn = siglip._loss_fn({"loss_fn": loss_fn})
+  dzimg, dztxt = fn(P, zi[rank * n:(rank + 1) * n].float(), zt[rank * n:(rank + 1) * n].float(),
+                    siglip.Dist(), scal)
   dist.all_reduce(scal)
   dist.all_reduce(P.g("t"))
   dist.all_reduce(P.g("b"))
@@ -87,12 +97,16 @@ def _worker(rank, world, port, ret):
   dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_sigmoid_loss_equals_global_loss(world):
-  port = 29500 + os.getpid() % 1000 + world
+@pytest.mark.parametrize("world,loss_fn", [(2, "sigmoid"), (3, "sigmoid"), (2, "chunked_sigmoid"),
+                                           (3, "chunked_sigmoid")])
+def test_sharded_sigmoid_loss_equals_global_loss(world, loss_fn):
+  """Both DP forms of the loss -- all-gather ([n,B] slab) and the paper's chunked rounds ([n,n]
+  blocks, broadcast from / reduce to the chunk's owner) -- reproduce the global-batch loss and
+  gradients (SURVEY 8e invariant)."""
+  port = 29500 + os.getpid() % 1000 + world + (10 if loss_fn != "sigmoid" else 0)
   ctx = mp.get_context("spawn")
   ret = ctx.Manager().dict()
-  procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+  procs = [ctx.Process(target=_worker, args=(r, world, port, ret, loss_fn)) for r in range(world)]
   for p in procs:
     p.start()
   for p in procs:

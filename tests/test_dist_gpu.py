@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, loss_fn="sigmoid"):
   sys.path.insert(0, ROOT)
   sys.path.insert(0, os.path.join(ROOT, "tests"))
   os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -30,7 +30,7 @@ def _worker(rank, world, port, ret):
   n = image.shape[0] // world
   img = torch.from_numpy(image[rank * n:(rank + 1) * n]).cuda()
   txt = torch.from_numpy(text[rank * n:(rank + 1) * n]).cuda()
-  loss, _ = siglip.loss_and_grads(model, P, img, txt)
+  loss, _ = siglip.loss_and_grads(model, P, img, txt, loss_fn=loss_fn)
   torch.cuda.synchronize()
   if rank == 0:
     ret["loss"] = float(loss)
@@ -39,14 +39,15 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_equals_single_rank_global_batch():
+@pytest.mark.parametrize("loss_fn", ["sigmoid", "chunked_sigmoid"])
+def test_two_rank_step_equals_single_rank_global_batch(loss_fn):
   import torch.multiprocessing as mp
   from big_vision_b200.models.proj.image_text import two_towers
   from big_vision_b200.trainers.proj.image_text import siglip
   ctx = mp.get_context("spawn")
   ret = ctx.Manager().dict()
-  port = 29700 + os.getpid() % 200
-  procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+  port = 29700 + os.getpid() % 200 + (7 if loss_fn != "sigmoid" else 0)
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, loss_fn)) for r in range(2)]
   for p in procs:
     p.start()
   for p in procs:

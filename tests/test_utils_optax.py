@@ -62,3 +62,13 @@ def test_get_mixup_draws_a_at_least_one_half():
     assert 0.5 <= a <= 1.0
     b = np.random.default_rng(seed).beta(0.2, 0.2)
     assert a == max(b, 1.0 - b)
+
+
+def test_siglip_loss_fn_selection():
+  """config.loss_fn as in _deprecated_contrastive.py:322-331; the softmax (CLIP) loss is not built."""
+  import pytest
+  from big_vision_b200.trainers.proj.image_text import siglip
+  assert siglip._loss_fn(None) is siglip.sigmoid_loss_fwd_bwd
+  assert siglip._loss_fn({"loss_fn": "chunked_sigmoid"}) is siglip.chunked_sigmoid_loss_fwd_bwd
+  with pytest.raises(NotImplementedError):
+    siglip._loss_fn({"loss_fn": "softmax"})
