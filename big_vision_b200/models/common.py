@@ -1,41 +1,39 @@
-"""Host-side helpers shared by the model modules (mirror of big_vision/models/common.py:24-92)."""
-import logging
+"""Host-side helpers shared by the model modules.
 
+`merge_params` has the contract of big_vision/models/common.py:24-92: the result has the structure
+of the freshly initialised tree and the checkpoint's values, except for names matched by a
+`dont_load` regex (those keep their init value and may be absent on either side); any other
+structural difference is an error that lists both sides.
+"""
 from big_vision_b200 import utils as u
 
 
+def _report(ckpt_names, model_names, only_model, only_ckpt):
+  def block(title, names, bullet="  "):
+    return [f"{title}:"] + [f"{bullet}{n}" for n in sorted(names)] if names else []
+  lines = (block("Params in checkpoint", ckpt_names) + block("Params in model (code)", model_names) +
+           block("Params in model (code) but not in checkpoint and not `dont_load`ed", only_model, " - ") +
+           block("Params in checkpoint but not in model (code) and not `dont_load`ed", only_ckpt, " + "))
+  return "\n".join(lines)
+
+
 def merge_params(loaded, inited, dont_load=(), match_dtype=False):
-  """Makes `loaded` match the structure of `inited`; names matching a `dont_load` regex keep their
-  init value (or may be missing on either side); any other mismatch raises with both key lists."""
-  if inited is None:
+  if inited is None:                 # nothing to match against (interactive use)
     return loaded
-  dont_load = u.check_and_compile_patterns(dont_load)
+  patterns = u.check_and_compile_patterns(dont_load)
+  exempt = lambda name: any(p.fullmatch(name) for p in patterns)
+  ckpt = dict(u.tree_flatten_with_names(loaded)[0])
+  model = dict(u.tree_flatten_with_names(inited)[0])
 
-  def should_merge(name):
-    return not any(pattern.fullmatch(name) for pattern in dont_load)
-
-  loaded_flat = dict(u.tree_flatten_with_names(loaded)[0])
-  inited_flat = dict(u.tree_flatten_with_names(inited)[0])
-  merged = {}
-  for name, init_val in inited_flat.items():
-    if name in loaded_flat and should_merge(name):
-      merged[name] = loaded_flat[name]
-      if match_dtype:
-        merged[name] = loaded_flat[name].astype(init_val.dtype)
+  out = {}
+  for name, init_val in model.items():
+    if name in ckpt and not exempt(name):
+      out[name] = ckpt[name].astype(init_val.dtype) if match_dtype else ckpt[name]
     else:
-      logging.info("Ignoring checkpoint and using init value for %s", name)
-      merged[name] = init_val
+      out[name] = init_val           # dont_load, or (checked below) missing from the checkpoint
 
-  def pp(title, names, indent="  "):
-    return f"{title}:\n" + "\n".join(f"{indent}{k}" for k in sorted(names)) if names else ""
-
-  not_in_loaded = {k for k in inited_flat.keys() - loaded_flat.keys() if should_merge(k)}
-  not_in_inited = {k for k in loaded_flat.keys() - inited_flat.keys() if should_merge(k)}
-  if not_in_loaded or not_in_inited:
-    raise ValueError(
-        pp("Params in checkpoint", loaded_flat.keys()) + "\n" +
-        pp("Params in model (code)", inited_flat.keys()) + "\n" +
-        pp("Params in model (code) but not in checkpoint and not `dont_load`ed", not_in_loaded, indent=" - ") +
-        "\n" +
-        pp("Params in checkpoint but not in model (code) and not `dont_load`ed", not_in_inited, indent=" + "))
-  return u.recover_tree(merged.keys(), merged.values())
+  only_model = [n for n in model if n not in ckpt and not exempt(n)]
+  only_ckpt = [n for n in ckpt if n not in model and not exempt(n)]
+  if only_model or only_ckpt:
+    raise ValueError(_report(ckpt.keys(), model.keys(), only_model, only_ckpt))
+  return u.recover_tree(list(out.keys()), list(out.values()))
