@@ -466,7 +466,15 @@ constexpr int BWD_STG_OFF = BWD_DS_OFF + 2 * TILE_BYTES;      // 16 KB output st
 constexpr int BWD_STAT_OFF = BWD_STG_OFF + TILE_BYTES;        // lse2[256], delta[256]
 constexpr int BWD_BAR_OFF = BWD_STAT_OFF + 4 * BWD_ROWS * 4;   // lse2 / delta, double-buffered per item
 constexpr int BWD_SMEM = BWD_BAR_OFF + 128 + 1024;
+constexpr int BWD_SMEM_PIPE = BWD_SMEM + 128;      // + per-tile operand barriers
 
+// PIPE = true (BV_ATTN_BWD_PIPE=1, bring-up; NOT yet validated on hardware): operands are loaded
+// and released per 128-row tile instead of per item, so the next item's K/V (and then Q/dO) tiles
+// stream in while the current item still works on its last key tile; single-tile items (the text
+// tower) alternate between the two tile slots of each operand, i.e. are double-buffered; S/dP of the
+// next item's first pair are issued ahead of the last gradient products when its operands have
+// landed; and delta / lse of item i+1 are fetched at the start of item i.
+template <bool PIPE>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -487,6 +495,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t dkv_full = bar + 64, dkv_empty = bar + 72, dq_full = bar + 80, dq_empty = bar + 88;
   const uint32_t tmem_slot = bar + 96;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + BWD_BAR_OFF + 96);
+  // PIPE: operand tile slots.  K and V tile t travel together (slot barrier "kv"), Q and dO too ("q")
+  auto full_kv = [&](int sl) { return bar + 128u + 8u * sl; };
+  auto empty_kv = [&](int sl) { return bar + 144u + 8u * sl; };
+  auto full_q = [&](int sl) { return bar + 160u + 8u * sl; };
+  auto empty_q = [&](int sl) { return bar + 176u + 8u * sl; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 8 && lane == 0) {
@@ -498,6 +511,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(pds_full, 8);  mbar_init(pds_empty, 1);
     mbar_init(dkv_full, 1);  mbar_init(dkv_empty, 4);   // *_empty: one arrive per write-out warp
     mbar_init(dq_full, 1);   mbar_init(dq_empty, 4);
+    if constexpr (PIPE) {
+      for (int sl = 0; sl < 2; ++sl) {
+        mbar_init(full_kv(sl), 1); mbar_init(empty_kv(sl), 1);
+        mbar_init(full_q(sl), 1);  mbar_init(empty_q(sl), 1);
+      }
+    }
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -599,7 +618,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (warp == 8) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    if (PIPE) {
+      if (lane == 0) {
+        // need-order of an item: K/V tile 0, Q/dO tiles, then K/V tile 1.  A slot is refilled as soon
+        // as the MMAs of its last use retired (empty_*), which for tile 0 of a two-tile operand is
+        // long before the item ends.  fills_* count the fills of each slot (barrier parity).
+        uint32_t fills_kv[2] = {0u, 0u}, fills_q[2] = {0u, 0u};
+        for (int it = 0; it < my_items; ++it) {
+          const int bh = blockIdx.x + it * gridDim.x;
+          const int h = bh % p.H, b = bh / p.H;
+          auto load_kv = [&](int t) {
+            const int sl = p.KT == 1 ? (it & 1) : t;
+            mbar_wait(empty_kv(sl), (fills_kv[sl] & 1u) ^ 1u);
+            ++fills_kv[sl];
+            mbar_expect_tx(full_kv(sl), 2 * TILE_BYTES);
+            tma_load_3d(k_s + sl * TILE_BYTES, &tmK, full_kv(sl), h * DH, t * TQ, b);
+            tma_load_3d(v_s + sl * TILE_BYTES, &tmV, full_kv(sl), h * DH, t * TQ, b);
+          };
+          auto load_q = [&](int t) {
+            const int sl = p.QT == 1 ? (it & 1) : t;
+            mbar_wait(empty_q(sl), (fills_q[sl] & 1u) ^ 1u);
+            ++fills_q[sl];
+            mbar_expect_tx(full_q(sl), 2 * TILE_BYTES);
+            tma_load_3d(do_s + sl * TILE_BYTES, &tmdO, full_q(sl), h * DH, t * TQ, b);
+            tma_load_3d(q_s + sl * TILE_BYTES, &tmQ, full_q(sl), h * DH, t * TQ, b);
+          };
+          load_kv(0);
+          for (int t = 0; t < p.QT; ++t) load_q(t);
+          if (p.KT > 1) load_kv(1);
+          BWD_DBG(13, it * 4);
+        }
+      }
+    } else if (lane == 0) {
       // Operands are single-buffered (shared memory is full), so every CTA alternates between an
       // HBM-bound load phase and a compute phase.  Left alone, all 148 CTAs fall into the same
       // phase and the loads of one burst share the HBM bandwidth.  Starting the odd CTAs half an
@@ -700,6 +750,95 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (lane == 0) BWD_DBG(6, grad_cnt - 1);
         if (last_q) ++kt_cnt;
       };
+      if constexpr (PIPE) {
+        // per-slot release counters (== fills consumed so far; parity of the slot's full barrier)
+        uint32_t use_kv[2] = {0u, 0u}, use_q[2] = {0u, 0u};
+        auto slot_kv = [&](int it, int kt) { return p.KT == 1 ? (it & 1) : kt; };
+        auto slot_q = [&](int it, int qt) { return p.QT == 1 ? (it & 1) : qt; };
+        // have the operands of pair 0 of item `it` landed?  (non-blocking)
+        auto first_pair_ready = [&](int it) {
+          const int skv = slot_kv(it, 0), sq = slot_q(it, 0);
+          const int ok = (mbar_test(full_kv(skv), use_kv[skv] & 1u) && mbar_test(full_q(sq), use_q[sq] & 1u)) ? 1 : 0;
+          return __shfl_sync(0xffffffffu, ok, 0) != 0;      // one answer for the whole warp
+        };
+        auto sdp_pipe = [&](int it, int j) {
+          const int kt = j / p.QT, qt = j % p.QT;
+          const int skv = slot_kv(it, kt), sq = slot_q(it, qt);
+          if (qt == 0) mbar_wait(full_kv(skv), use_kv[skv] & 1u);   // first use of this K/V tile
+          if (kt == 0) mbar_wait(full_q(sq), use_q[sq] & 1u);       // first use of this Q/dO tile
+          mbar_wait(sdp_empty, (sdp_cnt & 1u) ^ 1u);
+          ++sdp_cnt;
+          tc_fence_after();
+          uint32_t qa = q_s + sq * TILE_BYTES, ka = k_s + skv * TILE_BYTES;
+          uint32_t va = v_s + skv * TILE_BYTES, da = do_s + sq * TILE_BYTES;
+          asm volatile("" : "+r"(qa), "+r"(ka), "+r"(va), "+r"(da));
+          const uint64_t dq_k = umma_smem_desc_sw128(qa, 16, 1024), dk_k = umma_smem_desc_sw128(ka, 16, 1024);
+          const uint64_t ddo_k = umma_smem_desc_sw128(da, 16, 1024), dv_k = umma_smem_desc_sw128(va, 16, 1024);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16_ss(tmem_base + S_COL, dq_k + k * 2, dk_k + k * 2, id_kk, k > 0 ? 1u : 0u);
+              umma_bf16_ss(tmem_base + DP_COL, ddo_k + k * 2, dv_k + k * 2, id_kk, k > 0 ? 1u : 0u);
+            }
+            umma_commit(sdp_full);
+          }
+          __syncwarp();
+          if (lane == 0) BWD_DBG(5, sdp_cnt - 1);
+        };
+        auto grads_pipe = [&](int it, int j) {
+          const int kt = j / p.QT, qt = j % p.QT;
+          const int skv = slot_kv(it, kt), sq = slot_q(it, qt);
+          const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+          uint32_t qa = q_s + sq * TILE_BYTES, ka = k_s + skv * TILE_BYTES;
+          uint32_t da = do_s + sq * TILE_BYTES, pa = p_s, dsa = ds_s;
+          asm volatile("" : "+r"(qa), "+r"(ka), "+r"(da), "+r"(pa), "+r"(dsa));
+          mbar_wait(pds_full, grad_cnt & 1u);
+          ++grad_cnt;
+          if (qt == 0) mbar_wait(dkv_empty, (kt_cnt & 1u) ^ 1u);
+          if (kt == 0 && qt == 0) mbar_wait(dq_empty, ph ^ 1u);
+          tc_fence_after();
+          const uint64_t dp_mn = umma_smem_desc_sw128(pa, TILE_BYTES, 1024);
+          const uint64_t dds_mn = umma_smem_desc_sw128(dsa, TILE_BYTES, 1024);
+          const uint64_t dds_k = umma_smem_desc_sw128(dsa, 16, 1024);
+          const uint64_t ddo_mn = umma_smem_desc_sw128(da, 8192, 1024);
+          const uint64_t dq_mn = umma_smem_desc_sw128(qa, 8192, 1024);
+          const uint64_t dk_mn = umma_smem_desc_sw128(ka, 8192, 1024);
+          const bool last_q = (qt == p.QT - 1), last_k = (kt == p.KT - 1);
+          if (elect_one()) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const uint32_t accv = (qt > 0 || jj > 0) ? 1u : 0u;
+              umma_bf16_ss(tmem_base + DV_COL, dp_mn + jj * 128, ddo_mn + jj * 128, id_mm, accv);
+              umma_bf16_ss(tmem_base + DK_COL, dds_mn + jj * 128, dq_mn + jj * 128, id_mm, accv);
+              umma_bf16_ss(tmem_base + DQ_COL + qt * DH, dds_k + (jj >> 2) * (TILE_BYTES / 16) + (jj & 3) * 2,
+                           dk_mn + jj * 128, id_km, (kt > 0 || jj > 0) ? 1u : 0u);
+            }
+            umma_commit(pds_empty);
+            if (last_q) { umma_commit(dkv_full); umma_commit(empty_kv(skv)); }   // K/V tile kt done
+            if (last_k) umma_commit(empty_q(sq));                                // Q/dO tile qt done
+            if (last_q && last_k) umma_commit(dq_full);                          // item done
+          }
+          __syncwarp();
+          if (lane == 0) BWD_DBG(6, grad_cnt - 1);
+          if (last_q) { ++kt_cnt; ++use_kv[skv]; }
+          if (last_k) ++use_q[sq];
+        };
+        if (my_items > 0) sdp_pipe(0, 0);
+        for (int it = 0; it < my_items; ++it) {
+          for (int j = 0; j < pairs; ++j) {
+            bool deferred = false;
+            if (j + 1 < pairs) {
+              sdp_pipe(it, j + 1);
+            } else if (it + 1 < my_items) {
+              // S/dP of the next item go ahead of this item's last gradient products only if its
+              // first tiles are already in shared memory; otherwise they follow them
+              if (first_pair_ready(it + 1)) sdp_pipe(it + 1, 0); else deferred = true;
+            }
+            grads_pipe(it, j);
+            if (deferred) sdp_pipe(it + 1, 0);
+          }
+        }
+      } else
       for (int it = 0; it < my_items; ++it) {
         const uint32_t ph = static_cast<uint32_t>(it) & 1u;
         mbar_wait(in_full, ph);
@@ -735,14 +874,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bf16* __restrict__ p_do = pin_reg(p.d_o);
     const long long p_ldo = p.ldo, p_bso = p.bso, p_lddo = p.lddo, p_bsdo = p.bsdo;
     const int wmode = pin_reg(p.variant) & 3;
-    for (int it = 0; it < my_items; ++it) {
-      const int bh = blockIdx.x + it * gridDim.x;
+    // ---- prologue of item `pit`: delta = rowsum(O o dO) and lse (log2 units) for its 256 row slots,
+    // straight from global memory while the TMA loads are in flight; buffers alternate per item
+    auto prologue = [&](int pit) {
+      const int bh = blockIdx.x + pit * gridDim.x;
       const int h = bh % pH, b = bh / pH;
-      const uint32_t ph = static_cast<uint32_t>(it) & 1u;
-      // ---- prologue: delta = rowsum(O o dO) and lse (log2 units) for the 256 row slots of this
-      // item, straight from global memory (one row per thread) while the TMA loads are in flight
-      float* lse2_i = lse2_s + (it & 1) * BWD_ROWS;
-      float* delta_i = delta_s + (it & 1) * BWD_ROWS;
+      float* lse2_i = lse2_s + (pit & 1) * BWD_ROWS;
+      float* delta_i = delta_s + (pit & 1) * BWD_ROWS;
       // Eight lanes share a row (16 B each), so one warp-wide load touches four full 128-byte
       // lines: 8x fewer L1 wavefronts than a row per thread.  That matters beyond this loop -- a
       // congested load pipe also delays the tcgen05.mma issue of the other warps (measured).
@@ -775,7 +913,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         lse2_i[tid] = tid < pNq ? p_lse[static_cast<int64_t>(bh) * pNq + tid] * LOG2E : INFINITY;
       }
-      named_bar_sync(2, 256);
+    };
+    if constexpr (PIPE) {
+      if (my_items > 0) prologue(0);
+    }
+    for (int it = 0; it < my_items; ++it) {
+      if constexpr (PIPE) {
+        // item i+1's statistics are fetched now, a whole item ahead of their use: the barrier
+        // orders them (written during item i-1) before this item's reads, and this item's reads of
+        // the other buffer (finished with item i-1's pairs) before the writes below
+        named_bar_sync(2, 256);
+        if (it + 1 < my_items) prologue(it + 1);
+      } else {
+        prologue(it);
+        named_bar_sync(2, 256);
+      }
+      const float* lse2_i = lse2_s + (it & 1) * BWD_ROWS;
+      const float* delta_i = delta_s + (it & 1) * BWD_ROWS;
       if (tid == 0) BWD_DBG(7, pair_cnt);
 
       for (int kt = 0; kt < pKT; ++kt) {
@@ -948,20 +1102,30 @@ int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
   { const char* e = getenv("BV_BWD_VARIANT"); p.variant = e ? atoi(e) : 0; }
   const int cols = a.H * DH;
   CUtensorMap tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV;
-  if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, BWD_ROWS))) return rc;
-  if ((rc = make_tmap_bnd(&tmK, a.k, cols, a.Nk, a.B, a.ldk, a.bsk, BWD_ROWS))) return rc;
-  if ((rc = make_tmap_bnd(&tmV, a.v, cols, a.Nk, a.B, a.ldv, a.bsv, BWD_ROWS))) return rc;
-  if ((rc = make_tmap_bnd(&tmO, a.o, cols, a.Nq, a.B, a.ldo, a.bso, BWD_ROWS))) return rc;
-  if ((rc = make_tmap_bnd(&tmdO, g.d_o, cols, a.Nq, a.B, g.lddo, g.bsdo, BWD_ROWS))) return rc;
+  // BV_ATTN_BWD_PIPE=1: per-tile operand pipeline (bring-up switch, see attn_bwd_kernel<PIPE>)
+  const bool pipe = [] { const char* e = getenv("BV_ATTN_BWD_PIPE"); return e && e[0] == '1'; }();
+  const uint32_t in_rows = pipe ? TQ : BWD_ROWS;       // operand boxes: one tile, or the whole item
+  if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, in_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmK, a.k, cols, a.Nk, a.B, a.ldk, a.bsk, in_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmV, a.v, cols, a.Nk, a.B, a.ldv, a.bsv, in_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmO, a.o, cols, a.Nq, a.B, a.ldo, a.bso, in_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmdO, g.d_o, cols, a.Nq, a.B, g.lddo, g.bsdo, in_rows))) return rc;
   if ((rc = make_tmap_bnd(&tmdQ, g.dq, cols, a.Nq, a.B, g.lddq, g.bsdq, TQ))) return rc;
   if ((rc = make_tmap_bnd(&tmdK, g.dk, cols, a.Nk, a.B, g.lddk, g.bsdk, TQ))) return rc;
   if ((rc = make_tmap_bnd(&tmdV, g.dv, cols, a.Nk, a.B, g.lddv, g.bsdv, TQ))) return rc;
-  rc = check_cuda(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       BWD_SMEM), "cudaFuncSetAttribute(attn_bwd)");
-  if (rc) return rc;
   const int sms = num_sms();
   const int grid = p.BH < sms ? p.BH : sms;
-  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV, p);
+  if (pipe) {
+    rc = check_cuda(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         BWD_SMEM_PIPE), "cudaFuncSetAttribute(attn_bwd pipe)");
+    if (rc) return rc;
+    attn_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM_PIPE, s>>>(tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV, p);
+    return check_cuda(cudaGetLastError(), "attn_bwd_kernel<pipe> launch");
+  }
+  rc = check_cuda(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       BWD_SMEM), "cudaFuncSetAttribute(attn_bwd)");
+  if (rc) return rc;
+  attn_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, s>>>(tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV, p);
   return check_cuda(cudaGetLastError(), "attn_bwd_kernel launch");
 }
 

@@ -134,6 +134,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // variants used to study how waiting warps disturb the tcgen05.mma issuer (see attention.cu):
 // mode bit0: one lane polls, the rest of the warp parks at __syncwarp; bit1: nanosleep between polls
 __device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, int mode) {
