@@ -614,7 +614,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (etid == 0) tma_store_wait<0>();
   } else if (warp >= 8) {
-    reg_dec<48>();
+    // PIPE: the issuer keeps more state (slot parities, next-item look-ahead): 64 registers, taken
+    // from the compute warps (168 instead of 176)
+    if constexpr (PIPE) reg_dec<64>(); else reg_dec<48>();
   }
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -622,23 +624,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) {
         // need-order of an item: K/V tile 0, Q/dO tiles, then K/V tile 1.  A slot is refilled as soon
         // as the MMAs of its last use retired (empty_*), which for tile 0 of a two-tile operand is
-        // long before the item ends.  fills_* count the fills of each slot (barrier parity).
-        uint32_t fills_kv[2] = {0u, 0u}, fills_q[2] = {0u, 0u};
+        // long before the item ends.  fills_* hold the parity of each slot's fill count.
+        uint32_t fills_kv = 0u, fills_q = 0u;      // bit sl = parity of the number of fills of slot sl
         for (int it = 0; it < my_items; ++it) {
           const int bh = blockIdx.x + it * gridDim.x;
           const int h = bh % p.H, b = bh / p.H;
           auto load_kv = [&](int t) {
             const int sl = p.KT == 1 ? (it & 1) : t;
-            mbar_wait(empty_kv(sl), (fills_kv[sl] & 1u) ^ 1u);
-            ++fills_kv[sl];
+            mbar_wait(empty_kv(sl), ((fills_kv >> sl) & 1u) ^ 1u);
+            fills_kv ^= 1u << sl;
             mbar_expect_tx(full_kv(sl), 2 * TILE_BYTES);
             tma_load_3d(k_s + sl * TILE_BYTES, &tmK, full_kv(sl), h * DH, t * TQ, b);
             tma_load_3d(v_s + sl * TILE_BYTES, &tmV, full_kv(sl), h * DH, t * TQ, b);
           };
           auto load_q = [&](int t) {
             const int sl = p.QT == 1 ? (it & 1) : t;
-            mbar_wait(empty_q(sl), (fills_q[sl] & 1u) ^ 1u);
-            ++fills_q[sl];
+            mbar_wait(empty_q(sl), ((fills_q >> sl) & 1u) ^ 1u);
+            fills_q ^= 1u << sl;
             mbar_expect_tx(full_q(sl), 2 * TILE_BYTES);
             tma_load_3d(do_s + sl * TILE_BYTES, &tmdO, full_q(sl), h * DH, t * TQ, b);
             tma_load_3d(q_s + sl * TILE_BYTES, &tmQ, full_q(sl), h * DH, t * TQ, b);
@@ -751,21 +753,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (last_q) ++kt_cnt;
       };
       if constexpr (PIPE) {
-        // per-slot release counters (== fills consumed so far; parity of the slot's full barrier)
-        uint32_t use_kv[2] = {0u, 0u}, use_q[2] = {0u, 0u};
+        // per-slot parity of the releases so far (== fills consumed; parity of the slot's full barrier),
+        // one bit per slot: indexed arrays would live in local memory
+        uint32_t use_kv = 0u, use_q = 0u;
         auto slot_kv = [&](int it, int kt) { return p.KT == 1 ? (it & 1) : kt; };
         auto slot_q = [&](int it, int qt) { return p.QT == 1 ? (it & 1) : qt; };
         // have the operands of pair 0 of item `it` landed?  (non-blocking)
         auto first_pair_ready = [&](int it) {
           const int skv = slot_kv(it, 0), sq = slot_q(it, 0);
-          const int ok = (mbar_test(full_kv(skv), use_kv[skv] & 1u) && mbar_test(full_q(sq), use_q[sq] & 1u)) ? 1 : 0;
+          const int ok = (mbar_test(full_kv(skv), (use_kv >> skv) & 1u) && mbar_test(full_q(sq), (use_q >> sq) & 1u)) ? 1 : 0;
           return __shfl_sync(0xffffffffu, ok, 0) != 0;      // one answer for the whole warp
         };
         auto sdp_pipe = [&](int it, int j) {
           const int kt = j / p.QT, qt = j % p.QT;
           const int skv = slot_kv(it, kt), sq = slot_q(it, qt);
-          if (qt == 0) mbar_wait(full_kv(skv), use_kv[skv] & 1u);   // first use of this K/V tile
-          if (kt == 0) mbar_wait(full_q(sq), use_q[sq] & 1u);       // first use of this Q/dO tile
+          if (qt == 0) mbar_wait(full_kv(skv), (use_kv >> skv) & 1u);   // first use of this K/V tile
+          if (kt == 0) mbar_wait(full_q(sq), (use_q >> sq) & 1u);       // first use of this Q/dO tile
           mbar_wait(sdp_empty, (sdp_cnt & 1u) ^ 1u);
           ++sdp_cnt;
           tc_fence_after();
@@ -820,8 +823,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           __syncwarp();
           if (lane == 0) BWD_DBG(6, grad_cnt - 1);
-          if (last_q) { ++kt_cnt; ++use_kv[skv]; }
-          if (last_k) ++use_q[sq];
+          if (last_q) { ++kt_cnt; use_kv ^= 1u << skv; }
+          if (last_k) use_q ^= 1u << sq;
         };
         if (my_items > 0) sdp_pipe(0, 0);
         for (int it = 0; it < my_items; ++it) {
@@ -858,7 +861,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp < 8) {
     // ---------------- compute warps ----------------
-    reg_inc<176>();
+    if constexpr (PIPE) reg_inc<168>(); else reg_inc<176>();
     const int quarter = warp & 3, hf = warp >> 2;
     const int row = quarter * 32 + lane;
     const int tid = threadIdx.x;
