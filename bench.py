@@ -1,15 +1,19 @@
-"""Benchmark of the SigLIP ViT-B/16 two-tower training step (BASELINE.json metric:
-image-text pairs/sec; config 4 at weak scaling: 1024 pairs per GPU, global batch 1024*N).
+"""Benchmarks of the B200 hot path: the SigLIP two-tower training step (BASELINE.json metric:
+image-text pairs/sec; config 4 at weak scaling: 1024 pairs per GPU, global batch 1024*N) and the
+other BASELINE.json configurations as `--workload`s.
 
-  python bench.py --gpus 1 --steps 8 --warmup 3
+  python bench.py --gpus 1 --steps 8 --warmup 3                       # config 4 (the headline)
+  python bench.py --workload vit_b16_cls | mixer_b16 | vit_s16 | siglip_l14_336
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port P bench.py --gpus N --steps K --warmup W
-  python bench.py --impl reference ...      # the reference's algorithm on the host cores (oracle port)
+  python bench.py --impl reference ...   # the reference's algorithm on the host cores (oracle port)
+  python bench.py --impl torch_gpu ...   # labelled stand-in for the JAX/XLA-GPU build (baseline/torch_gpu.py)
 
-A "step" = update_fn: two-tower forward, pairwise sigmoid loss over all-gathered text
-embeddings, backward, gradient all-reduce, fused Adam.  Rank 0 prints ONE JSON line.
+A "step" = update_fn: forward, loss, backward, gradient all-reduce, fused Adam (for SigLIP: two-tower
+forward, pairwise sigmoid loss over all-gathered text embeddings).  Rank 0 prints ONE JSON line.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -20,19 +24,56 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MODEL_KW = dict(
-    image=dict(variant="B/16", pool_type="map"),
-    text=dict(variant="B", vocab_size=32_000),
-    out_dim=(None, 768), temperature_init=10.0, bias_init=-10.0)
 OPT_CONFIG = dict(optax_name="scale_by_adam", optax=dict(b2=0.95, mu_dtype="bfloat16"), lr=1e-3,
                   wd=1e-4, grad_clip_norm=1.0, schedule=dict(decay_type="cosine", warmup_steps=10))
-RES, TXT_LEN = 224, 64
-# algorithmic training FLOPs per image-text pair (3 x forward; SURVEY.md 8d / BASELINE.md 3)
-FLOPS_PER_PAIR = 139.3e9
-WORKLOAD = ("SigLIP two_towers ViT-B/16 (map pool) + text-B (64 tok, vocab 32000), 224x224, full update_fn "
-            "(fwd, sigmoid loss over gathered ztxt, bwd, grad all-reduce, Adam)")
-# ncu-measured DRAM traffic per GEMM launch (all GEMM launches of one bench run, see profiles/)
+TXT_LEN = 64
+
+# BASELINE.json configs -> workloads.  flops = algorithmic training FLOPs per sample (3 x forward;
+# SURVEY.md 8d / BASELINE.md 3).  per_gpu_batch is the weak-scaling shard (config 4: 8192 / 8).
+WORKLOADS = {
+    "siglip_b16": dict(          # config 4 -- the headline metric
+        kind="siglip", metric="siglip_vit_b16_pairs_per_sec", unit="pairs/s", res=224, per_gpu_batch=1024,
+        flops=139.3e9, model_kw=dict(image=dict(variant="B/16", pool_type="map"),
+                                     text=dict(variant="B", vocab_size=32_000),
+                                     out_dim=(None, 768), temperature_init=10.0, bias_init=-10.0),
+        oracle=dict(image=dict(depth=12, num_heads=12, pool_type="map", posemb="learn", rep_size=False,
+                               num_classes=None),
+                    text=dict(depth=12, num_heads=12, pool_type="last", num_classes=768)),
+        desc="SigLIP two_towers ViT-B/16 (map pool) + text-B (64 tok, vocab 32000), 224x224, full update_fn "
+             "(fwd, sigmoid loss over gathered ztxt, bwd, grad all-reduce, Adam)"),
+    "siglip_l14_336": dict(      # config 5
+        kind="siglip", metric="siglip_vit_l14_336_pairs_per_sec", unit="pairs/s", res=336, per_gpu_batch=2048,
+        flops=1268e9, remat=True,
+        model_kw=dict(image=dict(variant="L/14", pool_type="map"), text=dict(variant="L", vocab_size=32_000),
+                      out_dim=(None, 1024), temperature_init=10.0, bias_init=-10.0),
+        oracle=dict(image=dict(depth=24, num_heads=16, pool_type="map", posemb="learn", rep_size=False,
+                               num_classes=None),
+                    text=dict(depth=24, num_heads=16, pool_type="last", num_classes=1024)),
+        desc="SigLIP two_towers ViT-L/14@336 (576 tokens, map pool) + text-L (64 tok), full update_fn with "
+             "per-block recompute (models/vit.py:129-148 nn.remat, nothing_saveable)"),
+    "vit_b16_cls": dict(         # config 2
+        kind="cls", model="vit", metric="vit_b16_cls_img_per_sec", unit="img/s", res=224, per_gpu_batch=256,
+        flops=105.4e9, num_classes=1000, loss="sigmoid_xent",
+        model_kw=dict(variant="B/16", rep_size=True, pool_type="tok"),
+        oracle=dict(depth=12, num_heads=12, pool_type="tok", posemb="learn", rep_size=True, num_classes=1000),
+        desc="ViT-B/16 ImageNet classification (configs/vit_i1k.py: cls token, rep_size, sigmoid_xent), "
+             "224x224, full update_fn"),
+    "mixer_b16": dict(           # config 3
+        kind="cls", model="mlp_mixer", metric="mixer_b16_img_per_sec", unit="img/s", res=224, per_gpu_batch=256,
+        flops=75.6e9, num_classes=1000, loss="sigmoid_xent", model_kw=dict(variant="B/16"),
+        oracle=dict(num_blocks=12, num_classes=1000),
+        desc="MLP-Mixer-B/16 (configs/mlp_mixer_i1k.py, sigmoid_xent, stoch_depth 0), 224x224, full update_fn"),
+    "vit_s16": dict(             # config 1 (the reference's CPU-runnable plumbing case)
+        kind="cls", model="vit", metric="vit_s16_img_per_sec", unit="img/s", res=224, per_gpu_batch=8,
+        flops=27.4e9, num_classes=1000, loss="softmax_xent",
+        model_kw=dict(variant="S/16", rep_size=True, pool_type="gap", posemb="sincos2d"),
+        oracle=dict(depth=12, num_heads=6, pool_type="gap", posemb="sincos2d", rep_size=True, num_classes=1000),
+        desc="ViT-S/16 (configs/vit_s16_i1k.py: gap, sincos2d, rep_size, softmax_xent), 224x224, batch 8, "
+             "full update_fn"),
+}
+# ncu-measured DRAM traffic per GEMM launch (all GEMM launches of one siglip_b16 bench run)
 NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 0.927e9
+NCU_GEMM_DRAM_SOURCE = "profiles/r01_final_launch_summary.md (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
 
 
 def measured_peaks():
@@ -93,57 +134,56 @@ class ClockSampler:
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_batch(n, seed):
+def synthetic_batch(wl, n, seed):
+  """SURVEY.md 8d synthetic inputs: images U(-1,1) fp32 NHWC; text ids U{2..31999} for a random length
+  then sticky EOS/pad id 1; class labels one-hot fp32 [n, 1000].  Returns dict of numpy arrays."""
   import numpy as np
   rng = np.random.default_rng(seed)
-  image = rng.uniform(-1, 1, size=(n, RES, RES, 3)).astype(np.float32)
-  text = np.ones((n, TXT_LEN), dtype=np.int32)
-  lens = rng.integers(4, TXT_LEN, size=n)
-  for i in range(n):
-    text[i, :lens[i]] = rng.integers(2, 32_000, size=lens[i])
-  return image, text
+  res = wl["res"]
+  # uniform fp32 in [-1, 1): generated in float32 directly (2.8 GB at config 5 would be 5.5 GB in f64)
+  image = rng.random(size=(n, res, res, 3), dtype=np.float32) * np.float32(2) - np.float32(1)
+  if wl["kind"] == "siglip":
+    text = np.ones((n, TXT_LEN), dtype=np.int32)
+    lens = rng.integers(4, TXT_LEN, size=n)
+    for i in range(n):
+      text[i, :lens[i]] = rng.integers(2, 32_000, size=lens[i])
+    return {"image": image, "labels": text}
+  C = wl["num_classes"]
+  labels = np.zeros((n, C), dtype=np.float32)
+  labels[np.arange(n), rng.integers(0, C, size=n)] = 1.0
+  return {"image": image, "labels": labels}
+
+
+def build_model(wl):
+  if wl["kind"] == "siglip":
+    from big_vision_b200.models.proj.image_text import two_towers
+    kw = dict(wl["model_kw"])
+    if wl.get("remat"):
+      kw["image"] = dict(kw["image"], scan=True)     # scan + remat(nothing_saveable): models/vit.py:129-148
+      kw["text"] = dict(kw["text"], scan=True)
+    return two_towers.Model(**kw)
+  import importlib
+  mod = importlib.import_module(f"big_vision_b200.models.{wl['model']}")
+  return mod.Model(wl["num_classes"], **wl["model_kw"])
+
+
+def init_params(wl, model, n, device):
+  shape = (n, wl["res"], wl["res"], 3)
+  if wl["kind"] == "siglip":
+    return model.init(0, shape, (n, TXT_LEN), device=device)
+  return model.init(0, shape, device=device)
 
 
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_port_step(pairs, threads=None):
-  """One fwd+bwd of the SigLIP B/16 loss on `pairs` pairs with the CPU oracle; returns seconds."""
-  import numpy as np
-  import torch
-  from oracle import bv_oracle as O
-  from big_vision_b200.models import vit
-  from big_vision_b200.models.proj.image_text import two_towers
-  if threads:
-    torch.set_num_threads(threads)
-  if not hasattr(cpu_port_step, "_state"):
-    model = two_towers.Model(**MODEL_KW)
-    P = model.init(0, (pairs, RES, RES, 3), (pairs, TXT_LEN), device="cpu")
-    tree = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in P.numpy_tree("f").items()}
-    cfg = {"image": dict(depth=12, num_heads=12, pool_type="map", posemb="learn", rep_size=False, num_classes=None),
-           "text": dict(depth=12, num_heads=12, pool_type="last", num_classes=768)}
-    cpu_port_step._state = (tree, cfg)
-  tree, cfg = cpu_port_step._state
-  image, text = synthetic_batch(pairs, 0)
-  t0 = time.perf_counter()
-  for v in tree.values():
-    v.grad = None
-  # the port in fp32 (the reference's CPU default dtype) -- same algorithm, float32 arithmetic
-  O.F64 = torch.float32
-  zimg, ztxt, ex = O.two_towers_forward(tree, torch.from_numpy(image), torch.from_numpy(text), cfg, "float32")
-  loss = O.siglip_loss(zimg, ztxt, ex["t"], ex["b"])
-  loss.backward()
-  O.F64 = torch.float64
-  return time.perf_counter() - t0
-
-
 def usable_host_threads():
-  """Threads the CPU legs may use: torch's default intra-op pool, capped by the scheduler affinity
-  and the cgroup CPU quota.  More threads than runnable CPUs makes the OpenMP barriers of these
-  small-batch ops spin against each other (observed: minutes per step instead of seconds)."""
+  """Threads the CPU legs may use: the CPUs this process may run on (scheduler affinity), capped by
+  the cgroup CPU quota.  NOT torch.get_num_threads(): torchrun exports OMP_NUM_THREADS=1, which made
+  the N>1 reference arm of round 1 run on one core.  More threads than runnable CPUs makes the OpenMP
+  barriers of these small-batch ops spin against each other (minutes per step instead of seconds)."""
   import math
-  import torch
-  n = torch.get_num_threads()
+  n = os.cpu_count() or 1
   try:
     n = min(n, len(os.sched_getaffinity(0)))
   except AttributeError:
@@ -157,78 +197,215 @@ def usable_host_threads():
   return max(1, n)
 
 
+class CpuPort:
+  """One full update step (fwd, loss, bwd, clip + Adam + decoupled weight decay) of the workload on a
+  bounded sample of the batch with the CPU oracle in fp32 -- the same per-step content as the GPU arm.
+  The optimizer restates optax.py:143-149 (clip_by_global_norm -> scale_by_adam -> lr -> wd on
+  `.*/kernel$`) with torch foreach ops over the oracle's parameter tree."""
+
+  def __init__(self, wl, samples, threads):
+    import re
+    import torch
+    from oracle import bv_oracle as O
+    torch.set_num_threads(threads)
+    self.wl, self.O, self.samples = wl, O, samples
+    model = build_model({**wl, "remat": False})
+    P = init_params(wl, model, samples, "cpu")
+    self.tree = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True)
+                 for k, v in P.numpy_tree("f").items()}
+    self.names = list(self.tree)
+    self.decay = [bool(re.match(r".*/kernel$", k)) for k in self.names]
+    self.mu = [torch.zeros_like(v) for v in self.tree.values()]
+    self.nu = [torch.zeros_like(v) for v in self.tree.values()]
+    self.count = 0
+    b = synthetic_batch(wl, samples, 0)
+    self.image, self.labels = torch.from_numpy(b["image"]), torch.from_numpy(b["labels"])
+
+  def step(self):
+    import torch
+    O, wl = self.O, self.wl
+    t0 = time.perf_counter()
+    for v in self.tree.values():
+      v.grad = None
+    O.F64 = torch.float32            # the port in fp32 (the reference's CPU default dtype)
+    try:
+      if wl["kind"] == "siglip":
+        zimg, ztxt, ex = O.two_towers_forward(self.tree, self.image, self.labels, wl["oracle"], "float32")
+        loss = O.siglip_loss(zimg, ztxt, ex["t"], ex["b"])
+      else:
+        fwd = O.vit_forward if wl["model"] == "vit" else O.mixer_forward
+        logits = fwd(self.tree, self.image, wl["oracle"], "float32")
+        loss = getattr(O, wl["loss"])(logits, self.labels)
+      loss.backward()
+    finally:
+      O.F64 = torch.float64
+    with torch.no_grad():
+      ps = list(self.tree.values())
+      gs = [p.grad if p.grad is not None else torch.zeros_like(p) for p in ps]
+      gn = torch.sqrt(sum((g * g).sum() for g in gs))
+      clip = OPT_CONFIG["grad_clip_norm"]
+      torch._foreach_mul_(gs, float(min(1.0, clip / (float(gn) + 1e-30))))
+      self.count += 1
+      b1, b2, eps = 0.9, OPT_CONFIG["optax"]["b2"], 1e-8
+      torch._foreach_mul_(self.mu, b1); torch._foreach_add_(self.mu, gs, alpha=1 - b1)
+      torch._foreach_mul_(self.nu, b2); torch._foreach_addcmul_(self.nu, gs, gs, value=1 - b2)
+      c1, c2 = 1 - b1 ** self.count, 1 - b2 ** self.count
+      den = torch._foreach_sqrt(torch._foreach_div(self.nu, c2))
+      torch._foreach_add_(den, eps)
+      upd = torch._foreach_div(torch._foreach_div(self.mu, c1), den)
+      lr, wd = OPT_CONFIG["lr"], OPT_CONFIG["wd"]
+      for p, u, dec in zip(ps, upd, self.decay):
+        p.add_(u, alpha=-lr)
+        if dec:
+          p.mul_(1 - lr * wd)
+    return time.perf_counter() - t0
+
+
+def cpu_sample_sizes(wl):
+  return 8 if wl["per_gpu_batch"] >= 8 else wl["per_gpu_batch"]
+
+
 def run_reference(args):
-  import torch
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
+  wl = WORKLOADS[args.workload]
   threads = usable_host_threads()
-  # Each step is a bounded sample of the workload: `pairs` image-text pairs through fwd + bwd of the
-  # oracle port.  K and W are honoured; the sample shrinks (8 -> 4 -> 2 -> 1 pairs) if the first
-  # step shows that W + K steps would not finish within ~3 minutes on this host.
-  pairs, budget_s = 8, 180.0
+  # Each step is a bounded sample of the workload: `samples` units through one full update step of
+  # the oracle port.  K and W are honoured; the sample shrinks (8 -> 4 -> 2 -> 1) if the first step
+  # shows that W + K steps would not finish within ~3 minutes on this host.
+  samples, budget_s = cpu_sample_sizes(wl), 180.0
+  if wl["res"] > 224:
+    samples = 2
   warmup = max(1, args.warmup)
   steps = max(1, args.steps)
-  t_first = cpu_port_step(pairs, threads)          # warm-up step 1 (allocations, MKL plans)
+  port = CpuPort(wl, samples, threads)
+  t_first = port.step()                              # warm-up step 1 (allocations, MKL plans)
   est = t_first * (warmup - 1 + steps)
-  while est > budget_s and pairs > 1:
-    pairs //= 2
+  while est > budget_s and samples > 1:
+    samples //= 2
     est /= 2
-  if est > budget_s:                               # pathological host: keep the run bounded anyway
+    port = CpuPort(wl, samples, threads)
+  if est > budget_s:                                 # pathological host: keep the run bounded anyway
     steps = max(1, int(budget_s / (est / (warmup - 1 + steps))) - (warmup - 1))
   for _ in range(warmup - 1):
-    cpu_port_step(pairs, threads)
-  t = sum(cpu_port_step(pairs, threads) for _ in range(steps))
-  val = pairs * steps / t
+    port.step()
+  t = sum(port.step() for _ in range(steps))
+  val = samples * steps / t
+  unit_name = "pairs" if wl["kind"] == "siglip" else "images"
+  sample = (f"{steps} steps x {samples} {unit_name}, oracle port (torch-CPU fp32): fwd + loss + bwd + "
+            "clip/Adam/weight-decay update -- the GPU arm's per-step content on a bounded sample of its batch")
   line = {
-      "impl": "reference", "metric": "siglip_vit_b16_pairs_per_sec", "value": val, "unit": "pairs/s",
+      "impl": "reference", "metric": wl["metric"], "value": val, "unit": wl["unit"],
       "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t / steps,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
       "data": "synthetic",
-      "config": {"workload": WORKLOAD, "global_batch": pairs, "parallelism": f"cpu{threads}",
-                 "sample": "fwd+bwd of the pairwise sigmoid loss through both towers on a bounded "
-                           "sample of the batch (no optimizer step)"},
-      "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": threads, "kind": "port",
-                       "sample": f"{steps} steps x {pairs} pairs, oracle port (torch-CPU fp32, no optimizer)"},
-      "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "config": {"workload": f"{args.workload}: {wl['desc']}", "global_batch": samples,
+                 "parallelism": f"cpu{threads}", "sample": sample},
+      "cpu_baseline": {"value": val, "unit": wl["unit"], "cores": threads, "kind": "port", "sample": sample},
+      "e2e": {"value": val, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
   print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
+# labelled GPU stand-in for the JAX/XLA-GPU build (baseline/torch_gpu.py)
+# ----------------------------------------------------------------------------------------------
+def run_torch_gpu(args):
+  import torch
+  import torch.distributed as dist
+  from baseline import torch_gpu as TG
+  wl = WORKLOADS[args.workload]
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  torch.backends.cuda.matmul.allow_tf32 = True
+  torch.backends.cudnn.allow_tf32 = True
+  n = args.per_gpu_batch or wl["per_gpu_batch"]
+  host = synthetic_batch(wl, n, seed=rank)
+  batch = {k: torch.from_numpy(v).cuda() for k, v in host.items()}
+  step, nparams = TG.make_step(wl, world, rank, dev)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  note = ""
+  try:
+    for _ in range(max(3, args.warmup)):
+      loss = step(batch)
+    barrier()
+  except torch.cuda.OutOfMemoryError:
+    # autograd keeps more per block than the hand-written backward; say so instead of shrinking silently
+    line = {"impl": "torch_gpu", "unavailable": f"out of memory at per-GPU batch {n} "
+            f"({torch.cuda.max_memory_allocated() / 2**30:.0f} GiB peak); rerun with --per-gpu-batch"}
+    if rank == 0:
+      print(json.dumps(line), flush=True)
+    return
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(args.steps):
+    loss = step(batch)
+  e1.record()
+  barrier()
+  t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms = float(t)
+  if rank == 0:
+    val = n * world * args.steps / (ms * 1e-3)
+    peaks, _ = measured_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    line = {
+        "impl": "torch_gpu", "label": "STAND-IN, not the reference: PyTorch eager, bf16 autocast, cuBLAS + "
+        "SDPA + fused Adam + DDP (baseline/torch_gpu.py); JAX/XLA-GPU is not installable on this box",
+        "metric": wl["metric"], "value": val, "unit": wl["unit"], "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "global_batch": n * world,
+                   "per_gpu_batch": n, "parallelism": f"dp{world}", "params": nparams,
+                   "final_loss": float(loss), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30},
+        "step_mfu": val / world * wl["flops"] / 1e12 / peak_tf, "note": note,
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+def measure_ours(args, wl, world, rank, local_rank):
+  """Builds the model, runs the device-resident and the end-to-end timed regions; returns a dict of
+  raw measurements.  Everything that owns device memory is local to this function, so it is released
+  before the stand-in baseline (a separate process) needs the HBM."""
   import torch
   import torch.distributed as dist
   from big_vision_b200 import lib as L
   from big_vision_b200 import ops
   from big_vision_b200 import optax as bv_optax
-  from big_vision_b200.models.proj.image_text import two_towers
-  from big_vision_b200.trainers.proj.image_text import siglip
-
-  world = int(os.environ.get("WORLD_SIZE", "1"))
-  rank = int(os.environ.get("RANK", "0"))
-  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-  if not torch.cuda.is_available():
-    raise SystemExit("bench.py needs a GPU (there is no CPU fallback for the kernels)")
-  torch.cuda.set_device(local_rank)
-  if world > 1:
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-  if L.load().bv_device_supported() != 1:
-    raise SystemExit("bench.py needs a compute-capability 10.x device")
-  n = args.per_gpu_batch
-  model = two_towers.Model(**MODEL_KW)
-  P = model.init(0, (n, RES, RES, 3), (n, TXT_LEN), device="cuda")
+  n = args.per_gpu_batch or wl["per_gpu_batch"]
+  model = build_model(wl)
+  P = init_params(wl, model, n, "cuda")
   tx, _ = bv_optax.make(OPT_CONFIG, P, sched_kw=dict(total_steps=10_000, batch_size=n * world,
                                                      data_size=10_000_000))
   state = {"params": P, "opt": tx.init(P)}
-  update_fn = siglip.make_update_fn(model, tx, OPT_CONFIG)
-  image_h, text_h = synthetic_batch(n, seed=rank)
-  image_pin = torch.from_numpy(image_h).pin_memory()
-  text_pin = torch.from_numpy(text_h).pin_memory()
-  image_d, text_d = image_pin.cuda(), text_pin.cuda()
-  batch = {"image": image_d, "labels": text_d}
+  if wl["kind"] == "siglip":
+    from big_vision_b200.trainers.proj.image_text import siglip
+    update_fn = siglip.make_update_fn(model, tx, OPT_CONFIG)
+  else:
+    from big_vision_b200 import train
+    update_fn = train.make_update_fn(model, tx, {**OPT_CONFIG, "loss": wl["loss"]})
+  host = synthetic_batch(wl, n, seed=rank)
+  pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+  del host
+  batch = {k: v.cuda() for k, v in pinned.items()}
 
   def barrier():
     if world > 1:
@@ -251,9 +428,9 @@ def run_ours(args):
     out = ops_gemm(a, b, **kw)
     e1.record()
     a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
-    M = a.shape[1] if a_mn else a.shape[0]
-    K = a.shape[0] if a_mn else a.shape[1]
-    N = b.shape[1] if b_mn else b.shape[0]
+    M = kw.get("M") or (a.shape[1] if a_mn else a.shape[0])
+    K = kw.get("K") or (a.shape[0] if a_mn else a.shape[1])
+    N = kw.get("N") or (b.shape[1] if b_mn else b.shape[0])
     gemm_flops[0] += 2.0 * M * N * K
     # algorithmic bytes of this launch: both operands once, every output once, the epilogue operand
     o = out[0] if isinstance(out, tuple) else out
@@ -274,11 +451,11 @@ def run_ours(args):
   ev1.record()
   barrier()
   ops.gemm = ops_gemm
-  launches = L.LAUNCHES[0] - launches0
-  ms = ev0.elapsed_time(ev1)
-  gemm_ms = sum(a.elapsed_time(b) for a, b in gemm_events)
-  clocks = sampler.stop() if rank == 0 else None
-  loss = float(m["training_loss"])
+  R = {"n": n, "launches": L.LAUNCHES[0] - launches0, "ms": ev0.elapsed_time(ev1),
+       "gemm_ms": sum(a.elapsed_time(b) for a, b in gemm_events), "gemm_flops": gemm_flops[0],
+       "gemm_bytes": gemm_bytes[0], "gemm_launches": len(gemm_events),
+       "clocks": sampler.stop() if rank == 0 else None, "loss": float(m["training_loss"])}
+  del gemm_events
 
   # ---- end to end: host buffers in, loss out, every step --------------------------------------
   # The public input API (input_pipeline.start_input_pipeline, the reference's prefetch-to-device
@@ -289,35 +466,27 @@ def run_ours(args):
 
   def host_batches(k=None):
     for _ in range(args.steps if k is None else k):
-      yield {"image": image_pin, "labels": text_pin}
+      yield pinned
 
+  n_pre = int(os.environ.get("BV_E2E_PREFETCH", "1"))
   # untimed warm-up of the end-to-end path itself (side stream, device slots of the prefetcher:
   # a first-use cudaMalloc would otherwise synchronise the device inside the timed region)
-  if os.environ.get("BV_E2E") != "serial":
-    for dev_batch in input_pipeline.start_input_pipeline(
-        host_batches(2), n_prefetch=int(os.environ.get("BV_E2E_PREFETCH", "1"))):
-      state, m = update_fn(state, None, dev_batch)
-    del dev_batch
-
+  for dev_batch in input_pipeline.start_input_pipeline(host_batches(2), n_prefetch=n_pre):
+    state, m = update_fn(state, None, dev_batch)
+  del dev_batch
   loss_host = torch.empty(args.steps, dtype=torch.float32).pin_memory()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
   e0.record()
-  if os.environ.get("BV_E2E") == "serial":     # A/B switch: copy, step, blocking read, in order
-    for i in range(args.steps):
-      image_d.copy_(image_pin, non_blocking=True)
-      text_d.copy_(text_pin, non_blocking=True)
-      state, m = update_fn(state, None, {"image": image_d, "labels": text_d})
-      loss_host[i] = m["training_loss"].item()
-  else:
-    n_pre = int(os.environ.get("BV_E2E_PREFETCH", "1"))
-    for i, dev_batch in enumerate(input_pipeline.start_input_pipeline(host_batches(), n_prefetch=n_pre)):
-      state, m = update_fn(state, None, dev_batch)
-      loss_host[i:i + 1].copy_(m["training_loss"].reshape(1), non_blocking=True)   # device -> host
+  for i, dev_batch in enumerate(input_pipeline.start_input_pipeline(host_batches(), n_prefetch=n_pre)):
+    state, m = update_fn(state, None, dev_batch)
+    loss_host[i:i + 1].copy_(m["training_loss"].reshape(1), non_blocking=True)   # device -> host
   e1.record()
   barrier()
-  ms_e2e = e0.elapsed_time(e1)
+  R["ms_e2e"] = e0.elapsed_time(e1)
+  R["h2d"] = sum(v.numel() * v.element_size() for v in pinned.values())
   assert bool(torch.isfinite(loss_host).all()), loss_host
+  del dev_batch
 
   if args.profile_calls:      # every rank runs the extra step (collectives); rank 0 prints
     import collections
@@ -349,56 +518,95 @@ def run_ours(args):
         tf = f"  {flops[k] / v * 1e-9:7.1f} TFLOP/s" if flops[k] else ""
         print(f"[profile-calls]   {k:44s} {v:8.2f} ms  n={cnt[k]:4d}{tf}", file=sys.stderr)
 
-  t = torch.tensor([ms, ms_e2e, gemm_ms], dtype=torch.float64, device="cuda")
+  R["peak_mem_gib"] = torch.cuda.max_memory_allocated() / 2**30
+  t = torch.tensor([R["ms"], R["ms_e2e"], R["gemm_ms"]], dtype=torch.float64, device="cuda")
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms, ms_e2e, gemm_ms = (float(x) for x in t.tolist())
+  R["ms"], R["ms_e2e"], R["gemm_ms"] = (float(x) for x in t.tolist())
+  return R
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  from big_vision_b200 import lib as L
+  wl = WORKLOADS[args.workload]
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a GPU (there is no CPU fallback for the kernels)")
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+  if L.load().bv_device_supported() != 1:
+    raise SystemExit("bench.py needs a compute-capability 10.x device")
+  R = measure_ours(args, wl, world, rank, local_rank)
+  gc.collect()
+  torch.cuda.empty_cache()
 
   if rank == 0:
+    n = R["n"]
     peaks, peak_src = measured_peaks()
-    pairs = n * world * args.steps
-    value = pairs / (ms * 1e-3)
-    e2e_val = pairs / (ms_e2e * 1e-3)
+    units = n * world * args.steps
+    value = units / (R["ms"] * 1e-3)
+    e2e_val = units / (R["ms_e2e"] * 1e-3)
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    gemm_tf = gemm_flops[0] / (gemm_ms * 1e-3) / 1e12
-    cpu = None
+    gemm_tf = R["gemm_flops"] / (R["gemm_ms"] * 1e-3) / 1e12
+    cpu = gpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-      steps_cpu, pairs_cpu = 2, 8
       nthr = usable_host_threads()
-      t_warm = cpu_port_step(pairs_cpu, nthr)
-      steps_cpu = max(1, min(steps_cpu, int(60.0 / max(t_warm, 1e-3))))
-      tt = sum(cpu_port_step(pairs_cpu, nthr) for _ in range(steps_cpu))
-      cpu = {"value": pairs_cpu * steps_cpu / tt, "unit": "pairs/s", "cores": nthr,
-             "kind": "port", "sample": f"{steps_cpu} steps x {pairs_cpu} pairs fwd+bwd, oracle port in "
-                                       "torch-CPU fp32 (no optimizer step)"}
+      samples = 2 if wl["res"] > 224 else cpu_sample_sizes(wl)
+      port = CpuPort(wl, samples, nthr)
+      t_warm = port.step()
+      steps_cpu = max(1, min(2, int(60.0 / max(t_warm, 1e-3))))
+      tt = sum(port.step() for _ in range(steps_cpu))
+      cpu = {"value": samples * steps_cpu / tt, "unit": wl["unit"], "cores": nthr, "kind": "port",
+             "sample": f"{steps_cpu} steps x {samples} samples, oracle port in torch-CPU fp32: fwd + loss + "
+                       "bwd + clip/Adam/weight-decay update (same per-step content as the GPU arm)"}
+      del port
+    if world == 1 and not args.no_gpu_baseline:
+      # the labelled stand-in for the JAX/XLA-GPU build, same box, same run, its own process
+      cmd = [sys.executable, os.path.abspath(__file__), "--impl", "torch_gpu", "--workload", args.workload,
+             "--steps", str(min(args.steps, 6)), "--warmup", "3"]
+      if args.per_gpu_batch:
+        cmd += ["--per-gpu-batch", str(args.per_gpu_batch)]
+      try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        gpu_base = json.loads(out.stdout.strip().splitlines()[-1])
+      except Exception as e:   # pylint: disable=broad-except
+        gpu_base = {"impl": "torch_gpu", "unavailable": f"{type(e).__name__}: {e}"[:300]}
+    seq = {"siglip": (wl["res"] // 16 if "B/16" in str(wl["model_kw"]) else wl["res"] // 14) ** 2 + TXT_LEN}
     line = {
-        "metric": "siglip_vit_b16_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": R["ms"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "global_batch": n * world, "per_gpu_batch": n, "seq_len": 196 + TXT_LEN,
-                   "parallelism": f"dp{world}", "l2_policy": "inputs (616 MB images/step) and "
-                   "activations (>70 GB) exceed the 126 MB L2; no explicit flush",
-                   "final_loss": loss},
-        "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": image_pin.numel() * 4 + text_pin.numel() * 4,
-                "d2h_bytes_per_step": 4},
-        "gpu_launches": launches,
+        "config": {"workload": f"{args.workload}: {wl['desc']}",
+                   "global_batch": n * world, "per_gpu_batch": n,
+                   "seq_len": seq.get(wl["kind"], (wl["res"] // 16) ** 2),
+                   "parallelism": f"dp{world}",
+                   "l2_policy": f"inputs ({R['h2d'] / 1e6:.0f} MB/step) and activations (GBs) exceed the "
+                                "126 MB L2; no explicit flush",
+                   "final_loss": R["loss"], "peak_mem_gib": R["peak_mem_gib"]},
+        "clocks": R["clocks"],
+        "e2e": {"value": e2e_val, "unit": wl["unit"], "ms_per_step": R["ms_e2e"] / args.steps,
+                "h2d_bytes_per_step": R["h2d"], "d2h_bytes_per_step": 4},
+        "gpu_launches": R["launches"],
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 persistent GEMM)",
                      "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
                      "peak_source": f"{peak_src} bf16_tflops_sustained",
                      # per launch, averaged over the step's GEMM launches (shapes differ)
-                     "launches_per_step": len(gemm_events) // args.steps,
-                     "flop_per_launch": gemm_flops[0] / len(gemm_events),
-                     "algorithmic_bytes_per_launch": gemm_bytes[0] / len(gemm_events),
-                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum over the GEMM "
-                                       "launches of profiles/r01_final_launch_summary.md",
-                     "gemm_share_of_step": gemm_ms / ms,
-                     "step_mfu": value / world * FLOPS_PER_PAIR / 1e12 / peak_tf},
+                     "launches_per_step": R["gemm_launches"] // args.steps,
+                     "flop_per_launch": R["gemm_flops"] / R["gemm_launches"],
+                     "algorithmic_bytes_per_launch": R["gemm_bytes"] / R["gemm_launches"],
+                     "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH if args.workload == "siglip_b16" else None,
+                     "traffic_source": ("NOT measured in this run: constant from " + NCU_GEMM_DRAM_SOURCE
+                                        if args.workload == "siglip_b16" else None),
+                     "gemm_share_of_step": R["gemm_ms"] / R["ms"],
+                     "step_mfu": value / world * wl["flops"] / 1e12 / peak_tf},
         "cpu_baseline": cpu,
+        "gpu_baseline": gpu_base,
     }
     print(json.dumps(line), flush=True)
   if world > 1:
@@ -410,14 +618,18 @@ def main():
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=8)
   ap.add_argument("--warmup", type=int, default=3)
-  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--per-gpu-batch", type=int, default=1024)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
+  ap.add_argument("--workload", default="siglip_b16", choices=sorted(WORKLOADS))
+  ap.add_argument("--per-gpu-batch", type=int, default=0, help="0 = the workload's BASELINE.json shard")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-gpu-baseline", action="store_true")
   ap.add_argument("--profile-calls", action="store_true",
                   help="time every C-ABI call of one extra step with CUDA events; breakdown on stderr")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)
+  elif args.impl == "torch_gpu":
+    run_torch_gpu(args)
   else:
     if args.warmup < 3:
       args.warmup = 3

@@ -144,23 +144,28 @@ int bv_concat_cls(const void* x, const float* cls, void* out, int64_t n, int32_t
 int bv_drop_cls(const void* x, void* out, int64_t n, int32_t N0, int32_t d, void* stream) {
   return launch_drop_cls(x, out, n, N0, d, S(stream));
 }
+int bv_row_select(const void* a, const void* b, const float* mask, void* out, int64_t n, int32_t N,
+                  int32_t d, void* stream) {
+  return launch_row_select(a, b, mask, out, n, N, d, S(stream));
+}
 int bv_transpose_tokens(const void* x, void* y, int64_t n, int32_t N, int32_t d, void* stream) {
   return launch_transpose_tokens(x, y, n, N, d, S(stream));
 }
 
 int bv_siglip_loss(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
                    const float* t_param, const float* b_param, int64_t global_B, void* G,
-                   int64_t ldg, float* loss, float* dt, float* db, void* stream) {
+                   int64_t ldg, float* loss, float* dt, float* db, float* partials_ws,
+                   void* stream) {
   return launch_siglip_loss_ew(dots, n, B, ld, row_offset, t_param, b_param, global_B, G, ldg,
-                               loss, dt, db, S(stream));
+                               loss, dt, db, partials_ws, S(stream));
 }
 int bv_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                    int64_t n, int32_t C, void* stream) {
-  return launch_sigmoid_xent(logits, labels, loss, dlogits, n, C, S(stream));
+                    float* row_loss_ws, int64_t n, int32_t C, void* stream) {
+  return launch_sigmoid_xent(logits, labels, loss, dlogits, row_loss_ws, n, C, S(stream));
 }
 int bv_softmax_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                    int64_t n, int32_t C, void* stream) {
-  return launch_softmax_xent(logits, labels, loss, dlogits, n, C, S(stream));
+                    float* row_loss_ws, int64_t n, int32_t C, void* stream) {
+  return launch_softmax_xent(logits, labels, loss, dlogits, row_loss_ws, n, C, S(stream));
 }
 
 int bv_adam_step(const bv_adam_args* a, void* stream) {

@@ -368,6 +368,25 @@ __global__ void drop_cls_kernel(const bf16* __restrict__ x, bf16* __restrict__ o
   }
 }
 
+// Per-sample residual gate of stochastic depth (models/mlp_mixer.py:52,55 with the mask of :173-177):
+//   out[b,t,:] = mask[b] != 0 ? a[b,t,:] : (b_or_null ? b_or_null[b,t,:] : 0)        (bf16, d % 8 == 0)
+// forward:  a = x + branch(x) (the fused residual epilogue), b = x   ->  x + mask * branch(x), exactly
+// backward: a = d out, b = null                                       ->  mask * d out (into the branch)
+__global__ void row_select_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                  const float* __restrict__ mask, bf16* __restrict__ out,
+                                  int64_t n, int64_t per_sample_vec) {
+  const int64_t total = n * per_sample_vec;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t smp = idx / per_sample_vec;
+    uint4 q;
+    if (mask[smp] != 0.f) q = reinterpret_cast<const uint4*>(a)[idx];
+    else if (b != nullptr) q = reinterpret_cast<const uint4*>(b)[idx];
+    else q = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(out)[idx] = q;
+  }
+}
+
 // out[b,t,c] = (res ? res[b,t,c] : 0) + y[b,c,t]   with y stored [n, d, Np]: inverse of
 // transpose_tokens fused with the residual add (models/mlp_mixer.py:51-52)
 __global__ void untranspose_add_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
@@ -514,6 +533,18 @@ int launch_untranspose_add(const void* y, const void* res, void* out, int64_t n,
                                                      reinterpret_cast<const bf16*>(res),
                                                      reinterpret_cast<bf16*>(out), N, d, Np);
   return check_launch("untranspose_add_kernel");
+}
+int launch_row_select(const void* a, const void* b, const float* mask, void* out, int64_t n, int N,
+                      int d, cudaStream_t s) {
+  if (n <= 0 || N <= 0 || d <= 0 || d % 8) { set_error("bv_row_select: need n,N,d > 0, d %% 8 == 0"); return BV_ERR_INVALID; }
+  const int64_t per = static_cast<int64_t>(N) * d / 8;
+  int64_t blocks = (n * per + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  row_select_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      reinterpret_cast<const bf16*>(a), reinterpret_cast<const bf16*>(b), mask,
+      reinterpret_cast<bf16*>(out), n, per);
+  return check_cuda(cudaGetLastError(), "row_select_kernel launch");
 }
 int launch_concat_cls(const void* x, const float* cls, void* out, int64_t n, int N0, int d,
                       cudaStream_t s) {

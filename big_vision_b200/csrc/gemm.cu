@@ -26,6 +26,8 @@
 #include "host_utils.h"
 #include "kernels.h"
 
+#include <atomic>
+
 #include <stdlib.h>
 
 namespace bv {
@@ -672,12 +674,17 @@ int launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   p.aux_row_mod = g.aux_row_mod;
 
   auto kern = gemm_kernel<BN, OUT_F32, EF, CTAS, AUXM>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // The dynamic-shared-memory opt-in is a per-DEVICE attribute of the kernel: cache it per device
+  // (one process may drive several GPUs from several host threads; the flags are atomics and a
+  // duplicate set by two racing threads is harmless).
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev < 0 || !attr_set[dev].load(std::memory_order_acquire)) {
     rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES), "cudaFuncSetAttribute(gemm)");
     if (rc) return rc;
-    attr_set = true;
+    if (dev >= 0) attr_set[dev].store(true, std::memory_order_release);
   }
   const int tiles_resident = p.total_tiles < slots ? p.total_tiles : slots;
   cudaLaunchConfig_t cfg = {};

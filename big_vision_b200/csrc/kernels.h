@@ -91,15 +91,18 @@ int launch_mixup(const float* x, float* out, int64_t n, int64_t row_elems, float
 int launch_axpby(const void* x, const void* y, void* out, int dtype, float a, float b, int64_t n,
                  cudaStream_t s);
 int launch_transpose_tokens(const void* x, void* y, int64_t n, int N, int d, cudaStream_t s);
+int launch_row_select(const void* a, const void* b, const float* mask, void* out, int64_t n, int N,
+                      int d, cudaStream_t s);
 
 // ---- losses (loss.cu)
 int launch_siglip_loss_ew(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
                           const float* t_param, const float* b_param, int64_t global_B, void* G,
-                          int64_t ldg, float* loss, float* dt, float* db, cudaStream_t s);
+                          int64_t ldg, float* loss, float* dt, float* db, float* partials,
+                          cudaStream_t s);
 int launch_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                        int64_t n, int C, cudaStream_t s);
+                        float* row_loss, int64_t n, int C, cudaStream_t s);
 int launch_softmax_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                        int64_t n, int C, cudaStream_t s);
+                        float* row_loss, int64_t n, int C, cudaStream_t s);
 
 // ---- optimizer (optim.cu)
 struct AdamArgs {

@@ -525,9 +525,9 @@ int launch_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, con
     break;
   switch (nch) {
     LN_BWD_CASE(1) LN_BWD_CASE(2) LN_BWD_CASE(3) LN_BWD_CASE(4)
-    LN_BWD_CASE(5) LN_BWD_CASE(6)
+    LN_BWD_CASE(5) LN_BWD_CASE(6) LN_BWD_CASE(7) LN_BWD_CASE(8)
     default:
-      set_error("bv_layernorm_bwd: d=%d > 1536 not supported yet", d);
+      set_error("bv_layernorm_bwd: d=%d > 2048 not supported", d);
       return BV_ERR_UNSUPPORTED;
   }
 #undef LN_BWD_CASE

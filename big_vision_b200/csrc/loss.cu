@@ -39,7 +39,7 @@ siglip_loss_kernel(const float* __restrict__ dots, int64_t n, int64_t B, int64_t
                    int64_t row_offset, const float* __restrict__ t_param,
                    const float* __restrict__ b_param, float inv_B, bf16* __restrict__ G,
                    int64_t ldg, float* __restrict__ loss, float* __restrict__ dt,
-                   float* __restrict__ db) {
+                   float* __restrict__ db, float* __restrict__ partials) {
   __shared__ float sh[96];
   const float t = __expf(t_param[0]);
   const float bias = b_param ? b_param[0] : 0.f;
@@ -71,16 +71,49 @@ siglip_loss_kernel(const float* __restrict__ dots, int64_t n, int64_t B, int64_t
   l_acc *= inv_B;
   block_reduce3(l_acc, t_acc, b_acc, sh);
   if (threadIdx.x == 0) {
-    atomicAdd(loss, l_acc);
-    if (dt) atomicAdd(dt, t_acc);
-    if (db) atomicAdd(db, b_acc);
+    if (partials != nullptr) {
+      // deterministic mode: one partial per block, summed in a fixed order by finish_sums_kernel
+      partials[blockIdx.x] = l_acc;
+      partials[gridDim.x + blockIdx.x] = t_acc;
+      partials[2 * gridDim.x + blockIdx.x] = b_acc;
+    } else {
+      atomicAdd(loss, l_acc);
+      if (dt) atomicAdd(dt, t_acc);
+      if (db) atomicAdd(db, b_acc);
+    }
+  }
+}
+
+// Fixed-order finishing pass of the deterministic mode: out[k] += sum_i part[k*count + i].  One
+// block; thread t sums elements t, t+256, ... in index order, then a fixed shared-memory tree.  The
+// result depends only on (count, values), never on which block of the producer finished first --
+// XLA's reductions are run-to-run deterministic and so is this path.
+__global__ void __launch_bounds__(256)
+finish_sums_kernel(const float* __restrict__ part, int64_t count, float* out0, float* out1,
+                   float* out2) {
+  __shared__ float sh[256];
+  float* outs[3] = {out0, out1, out2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (outs[k] == nullptr) continue;          // uniform across the block
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < count; i += 256) acc += part[k * count + i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (static_cast<int>(threadIdx.x) < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) outs[k][0] += sh[0];
+    __syncthreads();
   }
 }
 
 // one warp per row
 __global__ void __launch_bounds__(256)
 sigmoid_xent_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
-                    float* __restrict__ loss, float* __restrict__ dlogits, int64_t n, int C) {
+                    float* __restrict__ loss, float* __restrict__ dlogits,
+                    float* __restrict__ row_loss, int64_t n, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -92,12 +125,15 @@ sigmoid_xent_kernel(const float* __restrict__ logits, const float* __restrict__ 
     if (dlogits) dlogits[row * C + c] = (sigmoid(x) - y) * inv_n;
   }
   acc = warp_sum(acc);
-  if (lane == 0) atomicAdd(loss, acc * inv_n);
+  if (lane == 0) {
+    if (row_loss != nullptr) row_loss[row] = acc * inv_n; else atomicAdd(loss, acc * inv_n);
+  }
 }
 
 __global__ void __launch_bounds__(256)
 softmax_xent_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
-                    float* __restrict__ loss, float* __restrict__ dlogits, int64_t n, int C) {
+                    float* __restrict__ loss, float* __restrict__ dlogits,
+                    float* __restrict__ row_loss, int64_t n, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -113,7 +149,10 @@ softmax_xent_kernel(const float* __restrict__ logits, const float* __restrict__ 
   se = warp_sum(se); sy = warp_sum(sy); sxy = warp_sum(sxy);
   const float lse = logf(se);
   // -sum y (x - lse) = lse * sum(y) - sum(y x)
-  if (lane == 0) atomicAdd(loss, (lse * sy - sxy) * inv_n);
+  if (lane == 0) {
+    const float rl = (lse * sy - sxy) * inv_n;
+    if (row_loss != nullptr) row_loss[row] = rl; else atomicAdd(loss, rl);
+  }
   if (dlogits) {
     for (int c = lane; c < C; c += 32) {
       const float x = logits[row * C + c] - mx, y = labels[row * C + c];
@@ -126,7 +165,8 @@ softmax_xent_kernel(const float* __restrict__ logits, const float* __restrict__ 
 
 int launch_siglip_loss_ew(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
                           const float* t_param, const float* b_param, int64_t global_B, void* G,
-                          int64_t ldg, float* loss, float* dt, float* db, cudaStream_t s) {
+                          int64_t ldg, float* loss, float* dt, float* db, float* partials,
+                          cudaStream_t s) {
   if (n <= 0 || B <= 0 || B % 4 || ld % 4 || ldg % 4 || global_B <= 0) {
     set_error("bv_siglip_loss: need n,B > 0 and B, ld, ldg multiples of 4");
     return BV_ERR_INVALID;
@@ -134,23 +174,35 @@ int launch_siglip_loss_ew(const float* dots, int64_t n, int64_t B, int64_t ld, i
   int64_t blocks = (n * (B / 4) + 255) / 256;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
+  if (blocks > BV_LOSS_WS_FLOATS / 3) blocks = BV_LOSS_WS_FLOATS / 3;
   siglip_loss_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
       dots, n, B, ld, row_offset, t_param, b_param, 1.0f / static_cast<float>(global_B),
-      reinterpret_cast<bf16*>(G), ldg, loss, dt, db);
-  return check_cuda(cudaGetLastError(), "siglip_loss_kernel launch");
+      reinterpret_cast<bf16*>(G), ldg, loss, dt, db, partials);
+  int rc = check_cuda(cudaGetLastError(), "siglip_loss_kernel launch");
+  if (rc || partials == nullptr) return rc;
+  finish_sums_kernel<<<1, 256, 0, s>>>(partials, blocks, loss, dt, db);
+  return check_cuda(cudaGetLastError(), "finish_sums_kernel launch");
 }
 
 int launch_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                        int64_t n, int C, cudaStream_t s) {
+                        float* row_loss, int64_t n, int C, cudaStream_t s) {
   if (n <= 0) return BV_OK;
-  sigmoid_xent_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(logits, labels, loss, dlogits, n, C);
-  return check_cuda(cudaGetLastError(), "sigmoid_xent_kernel launch");
+  sigmoid_xent_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(logits, labels, loss, dlogits,
+                                                                        row_loss, n, C);
+  int rc = check_cuda(cudaGetLastError(), "sigmoid_xent_kernel launch");
+  if (rc || row_loss == nullptr) return rc;
+  finish_sums_kernel<<<1, 256, 0, s>>>(row_loss, n, loss, nullptr, nullptr);
+  return check_cuda(cudaGetLastError(), "finish_sums_kernel launch");
 }
 int launch_softmax_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                        int64_t n, int C, cudaStream_t s) {
+                        float* row_loss, int64_t n, int C, cudaStream_t s) {
   if (n <= 0) return BV_OK;
-  softmax_xent_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(logits, labels, loss, dlogits, n, C);
-  return check_cuda(cudaGetLastError(), "softmax_xent_kernel launch");
+  softmax_xent_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(logits, labels, loss, dlogits,
+                                                                        row_loss, n, C);
+  int rc = check_cuda(cudaGetLastError(), "softmax_xent_kernel launch");
+  if (rc || row_loss == nullptr) return rc;
+  finish_sums_kernel<<<1, 256, 0, s>>>(row_loss, n, loss, nullptr, nullptr);
+  return check_cuda(cudaGetLastError(), "finish_sums_kernel launch");
 }
 
 }  // namespace bv

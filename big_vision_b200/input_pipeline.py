@@ -50,6 +50,9 @@ def start_input_pipeline(data, n_prefetch=1, device="cuda"):
     if slots[k] is None or any(slots[k][n].shape != h.shape or slots[k][n].dtype != h.dtype
                                for n, h in host.items()):
       slots[k] = {n: torch.empty(h.shape, dtype=h.dtype, device=dev) for n, h in host.items()}
+      # The caching allocator may hand back a block that main-stream kernels still queued behind the
+      # host are going to touch: the first copy into a NEW slot must wait for the main stream.
+      copy_stream.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(copy_stream):
       if consumed[k] is not None:
         copy_stream.wait_event(consumed[k])

@@ -73,12 +73,13 @@ SIGNATURES = {
     "bv_axpby": [c_vp, c_vp, c_vp, c_i32, c_f32, c_f32, c_i64, c_vp],
     "bv_transpose_tokens": [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "bv_untranspose_add": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
+    "bv_row_select": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "bv_concat_cls": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "bv_drop_cls": [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "bv_siglip_loss": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp,
-                       c_vp, c_vp],
-    "bv_sigmoid_xent": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
-    "bv_softmax_xent": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
+                       c_vp, c_vp, c_vp],
+    "bv_sigmoid_xent": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
+    "bv_softmax_xent": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
     "bv_adam_step": [ctypes.POINTER(AdamArgs), c_vp],
     "bv_sumsq": [c_vp, c_vp, c_i64, c_vp],
     "bv_top1": [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
@@ -122,7 +123,9 @@ def check(rc, what):
 
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES = [0]
-_LAUNCHES_PER_CALL = {"bv_embed_bwd": 2, "bv_retrieval_ranks": 2}
+_LAUNCHES_PER_CALL = {"bv_embed_bwd": 2, "bv_retrieval_ranks": 2, "bv_siglip_loss": 2,
+                      "bv_sigmoid_xent": 2, "bv_softmax_xent": 2}
+LOSS_WS_FLOATS = 8192      # BV_LOSS_WS_FLOATS
 
 
 # optional in-situ timing of every C-ABI call (bench.py --profile-calls): list of (name, e0, e1)

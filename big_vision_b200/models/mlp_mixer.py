@@ -6,8 +6,11 @@ The reference is fp32-only; BASELINE.json config 3 asks for bf16 matmuls (fp32 a
 is what runs here.  Token mixing applies the MLP along the token axis (mlp_mixer.py:49-51): the
 activations are transposed to [n*d, tokens] (tokens padded to a multiple of 8 for TMA strides), run
 through the same tcgen05 GEMMs, and transposed back fused with the residual add.
-stoch_depth must be 0 (the per-sample Bernoulli mask of mlp_mixer.py:173-177 needs JAX's RNG for
-parity; the benchmark/parity configs set it to 0).
+Stochastic depth (mlp_mixer.py:52,55,76,173-177): block i drops each residual branch per sample with
+probability i/(L-1)*stoch_depth, no 1/(1-p) rescale.  The 0/1 masks are an INPUT of fwd
+(`masks` fp32 [num_blocks, 2, n]; parity tests feed the same masks to the oracle) or, with train=True,
+are drawn from the numpy Generator passed as `rng` (the reference draws them from JAX's threefry
+stream, which cannot be reproduced without JAX).
 """
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -52,9 +55,18 @@ class MlpMixer:
   stoch_depth: float = 0.0
 
   def __post_init__(self):
-    if self.stoch_depth:
-      raise NotImplementedError("stoch_depth > 0 (needs the reference RNG for parity)")
     self._geom = None
+
+  def drop_p(self, i):
+    """mlp_mixer.py:76"""
+    return (i / max(self.num_blocks - 1, 1)) * self.stoch_depth
+
+  def draw_masks(self, rng, n, device):
+    """1 - Bernoulli(drop_p_i) per block, branch and sample (mlp_mixer.py:173-177) from a numpy
+    Generator; fp32 [num_blocks, 2, n] on `device`."""
+    p = np.array([self.drop_p(i) for i in range(self.num_blocks)], dtype=np.float64)[:, None, None]
+    keep = (rng.random((self.num_blocks, 2, n)) >= p).astype(np.float32)
+    return torch.from_numpy(keep).to(device)
 
   def specs(self, image_hw, in_ch=3):
     ph, pw = self.patch_size
@@ -95,12 +107,16 @@ class MlpMixer:
     """Name of the stored kernel/bias (padded storage if it exists)."""
     return p + what + ("_pad" if (p + what + "_pad") in P.offsets else "")
 
-  def fwd(self, P, image):
+  def fwd(self, P, image, *, train=False, rng=None, masks=None):
     n = image.shape[0]
     d, N, Np, T = self.hidden_dim, self._N, self._Np, self.tokens_mlp_dim
+    if masks is None and train and self.stoch_depth:
+      if rng is None:
+        raise ValueError("stoch_depth > 0 in training needs an rng (numpy Generator) or explicit masks")
+      masks = self.draw_masks(rng, n, image.device)
     patches = ops.patchify(image, self.patch_size[0])
     x = ops.gemm(patches, P.h("stem/kernel_flat"), b_mn=True, bias=P.f("stem/bias"))
-    saved = {"patches": patches, "n": n, "blocks": []}
+    saved = {"patches": patches, "n": n, "blocks": [], "masks": masks}
     for i in range(self.num_blocks):
       p = f"MixerBlock_{i}/"
       tm, cm = p + "token_mixing/", p + "channel_mixing/"
@@ -112,8 +128,12 @@ class MlpMixer:
       ops.gemm(hact, P.h(self._store(P, tm + "Dense_1/", "kernel")), b_mn=True,
                bias=P.f(self._store(P, tm + "Dense_1/", "bias")), out=ot, N=N)
       x1 = ops.untranspose_add(ot, x, n, N, d)
+      if masks is not None:
+        x1 = ops.row_select(x1, x, masks[i, 0], n, N)                         # x + mask * branch
       y2, mean2, rstd2 = ops.layernorm_fwd(x1, P.f(p + "LayerNorm_1/scale"), P.f(p + "LayerNorm_1/bias"))
-      x2, mlp_saved = vit.mlp_fwd(P, cm, y2, x1)
+      x2, mlp_saved = vit.mlp_fwd(vit.Scope(P, cm), y2, x1)
+      if masks is not None:
+        x2 = ops.row_select(x2, x1, masks[i, 1], n, N)
       saved["blocks"].append((x, mean1, rstd1, yt, hact, hpre, x1, mean2, rstd2, mlp_saved))
       x = x2
     y, mean, rstd = ops.layernorm_fwd(x, P.f("pre_head_layer_norm/scale"), P.f("pre_head_layer_norm/bias"))
@@ -136,22 +156,27 @@ class MlpMixer:
       dout = ops.gemm(d16, P.h("head/kernel"), out_dtype=torch.float32)
     dy = ops.pool_bwd(dout, n, N, 0)
     x, mean, rstd = saved["norm"]
+    masks = saved.get("masks")
+    # with stochastic depth the gradient entering a branch is mask * dx, so the fused
+    # "colsum(dx) -> the previous block's Dense_1 bias gradient" shortcut does not apply
     last = f"MixerBlock_{self.num_blocks - 1}/channel_mixing/Dense_1/bias"
     dx = ops.layernorm_bwd(dy, x, P.f("pre_head_layer_norm/scale"), mean, rstd,
                            dscale=P.g("pre_head_layer_norm/scale"), dbias=P.g("pre_head_layer_norm/bias"),
-                           dx_colsum=P.g(last))
+                           dx_colsum=P.g(last) if masks is None else None)
     for i in reversed(range(self.num_blocks)):
       p = f"MixerBlock_{i}/"
       tm, cm = p + "token_mixing/", p + "channel_mixing/"
       x, mean1, rstd1, yt, hact, hpre, x1, mean2, rstd2, mlp_saved = saved["blocks"][i]
       saved["blocks"][i] = None
       # channel mixing (colsum(dx) already went into this block's channel_mixing/Dense_1/bias)
-      dy2 = vit.mlp_bwd(P, cm, dx, mlp_saved, want_bias2_grad=False)
+      dbr = dx if masks is None else ops.row_select(dx, None, masks[i, 1], n, N)
+      dy2 = vit.mlp_bwd(vit.Scope(P, cm), dbr, mlp_saved, want_bias2_grad=masks is not None)
       dx1 = ops.layernorm_bwd(dy2, x1, P.f(p + "LayerNorm_1/scale"), mean2, rstd2, dres=dx,
                               dscale=P.g(p + "LayerNorm_1/scale"), dbias=P.g(p + "LayerNorm_1/bias"))
       # token mixing
       k1, b1 = self._store(P, tm + "Dense_1/", "kernel"), self._store(P, tm + "Dense_1/", "bias")
-      dot = ops.transpose_tokens(dx1, n, N, d)                                # [n*d, Np], pad = 0
+      dbr = dx1 if masks is None else ops.row_select(dx1, None, masks[i, 0], n, N)
+      dot = ops.transpose_tokens(dbr, n, N, d)                                # [n*d, Np], pad = 0
       ops.colsum(dot, P.g(b1))
       ops.gemm(hact, dot, a_mn=True, b_mn=True, out=P.g(k1), reduce_out=True, N=N)
       dhpre = ops.gemm(dot, P.h(k1), aux=hpre, epilogue=L.EPI_DGELU, K=N)    # [n*d, T]
@@ -161,6 +186,8 @@ class MlpMixer:
       ops.gemm(dhpre, P.h(tm + "Dense_0/kernel"), out=dyt, N=N)
       dyl = ops.untranspose_add(dyt, None, n, N, d)
       prev = (P.g(f"MixerBlock_{i - 1}/channel_mixing/Dense_1/bias") if i > 0 else P.g("stem/bias"))
+      if masks is not None and i > 0:
+        prev = None
       dx = ops.layernorm_bwd(dyl, x, P.f(p + "LayerNorm_0/scale"), mean1, rstd1, dres=dx1,
                              dscale=P.g(p + "LayerNorm_0/scale"), dbias=P.g(p + "LayerNorm_0/bias"),
                              dx_colsum=prev)

@@ -41,7 +41,7 @@ class _Model:
       raise NotImplementedError(f"Cannot do pooling '{self.pool_type}' on this path yet")
     self.prefix = (self.name + "/") if self.name else ""
     self.encoder = vit.Encoder(self.prefix + "Encoder_0/", self.depth, self.width,
-                               self.mlp_dim, self.num_heads)
+                               self.mlp_dim, self.num_heads, scan=self.scan, remat_policy=self.remat_policy)
     self._len = None
 
   def specs(self, text_len):
@@ -126,16 +126,20 @@ def Model(num_classes, *, variant=None, **kw):  # pylint: disable=invalid-name
 
 
 def load(init_params, init_file, model_cfg, dont_load=()):
-  """Init from a checkpoint -- models/proj/image_text/text_transformer.py:107-119 (including the
-  fix for old checkpoints that carried a second position embedding inside the encoder)."""
-  del model_cfg
+  """Text-tower parameters from a checkpoint (contract of text_transformer.py:107-119).  Early
+  checkpoints carry a SECOND position embedding inside the encoder, applied right after the
+  top-level one; the two tables are summed into the top-level parameter.  The encoder is (un)stacked
+  to match `model_cfg["scan"]`."""
   from big_vision_b200 import utils
   from big_vision_b200.models import common
-  params = dict(utils.load_params(init_file))
-  enc = dict(params["Encoder_0"])
-  extra_posemb = enc.pop("pos_embedding", 0)
-  params["Encoder_0"] = enc
-  params["pos_embedding"] = params["pos_embedding"] + extra_posemb
-  if "encoderblock" in enc:       # scan-stacked checkpoint into this (Python-loop) implementation
-    params = vit.scan_to_pyloop(params, encoder="Encoder_0")
-  return common.merge_params(params, init_params, dont_load)
+  tree = dict(utils.load_params(init_file))
+  encoder = dict(tree["Encoder_0"])
+  inner_table = encoder.pop("pos_embedding", None)
+  if inner_table is not None:
+    tree["pos_embedding"] = tree["pos_embedding"] + inner_table
+  tree["Encoder_0"] = encoder
+  stored_scanned = "encoderblock" in encoder
+  if bool((model_cfg or {}).get("scan")) != stored_scanned:
+    convert = vit.scan_to_pyloop if stored_scanned else vit.pyloop_to_scan
+    tree = convert(tree, encoder="Encoder_0")
+  return common.merge_params(tree, init_params, dont_load)

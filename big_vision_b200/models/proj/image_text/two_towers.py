@@ -87,33 +87,41 @@ class Model:
     return zimg, ztxt, out
 
 
-def load(init_params, init_files, model_cfg, img_load_kw={}, txt_load_kw={}):  # pylint: disable=dangerous-default-value
-  """Loads both towers (+ t, b) -- models/proj/image_text/two_towers.py:92-135.  `init_files` is a
-  single two-tower .npz path or a dict with img / txt / t / b entries ('file.npz:subtree')."""
+# which entry of `init_files` feeds which part of the model: (part, accepted keys)
+_LOAD_SOURCES = (("img", ("image", "img")), ("txt", ("text", "txt")), ("t", ("temperature", "t")),
+                 ("b", ("bias", "b")))
+_DEFAULT_TOWER = {"img": ("image_model", "vit", "image"),
+                  "txt": ("text_model", "proj.image_text.text_transformer", "text")}
+
+
+def load(init_params, init_files, model_cfg, img_load_kw=None, txt_load_kw=None):
+  """Two-tower parameters from checkpoints (contract of two_towers.py:92-135).
+
+  `init_files`: the path of ONE two-tower .npz -- its `img`, `txt`, `t` (and, for models with a
+  bias, `b`) sub-trees are used -- or a dict naming a source per part ("image"/"img",
+  "text"/"txt", "temperature"/"t", "bias"/"b", each "file.npz[:sub/tree]"); parts without a source
+  keep their value from `init_params`.  Each tower is loaded by its own module's `load` with the
+  tower's config and `img_load_kw` / `txt_load_kw` (e.g. dont_load).  Unknown keys are an error."""
   from big_vision_b200 import utils
   if isinstance(init_files, str):
-    keys = ("img", "txt", "t", "b") if "bias_init" in model_cfg.keys() else ("img", "txt", "t")
-    init_files = {k: f"{init_files}:{k}" for k in keys}
+    parts = [part for part, _ in _LOAD_SOURCES if part != "b" or "bias_init" in model_cfg.keys()]
+    sources = {part: f"{init_files}:{part}" for part in parts}
   else:
-    init_files = {**init_files}
-  if not init_params:
-    init_params = {"img": None, "txt": None}
-  restored = {**init_params}
-  img_init = init_files.pop("image", init_files.pop("img", None))
-  if img_init:
-    mod = importlib.import_module(f"big_vision_b200.models.{model_cfg.get('image_model', 'vit')}")
-    restored["img"] = mod.load(init_params["img"], img_init, model_cfg.get("image", {}), **img_load_kw)
-  txt_init = init_files.pop("text", init_files.pop("txt", None))
-  if txt_init:
-    mod = importlib.import_module(
-        f"big_vision_b200.models.{model_cfg.get('text_model', 'proj.image_text.text_transformer')}")
-    restored["txt"] = mod.load(init_params["txt"], txt_init, model_cfg.get("text", {}), **txt_load_kw)
-  t_init = init_files.pop("temperature", init_files.pop("t", None))
-  if t_init:
-    restored["t"] = utils.load_params(t_init)
-  b_init = init_files.pop("bias", init_files.pop("b", None))
-  if b_init:
-    restored["b"] = utils.load_params(b_init)
-  assert not init_files, (f"There's something unused left in `config.model_init`. You probably got "
-                          f"a typo. Here it is: {init_files}")
-  return restored
+    sources = dict(init_files)
+  init_params = init_params or {"img": None, "txt": None}
+  result = dict(init_params)
+  tower_kw = {"img": img_load_kw or {}, "txt": txt_load_kw or {}}
+  for part, keys in _LOAD_SOURCES:
+    found = [sources.pop(k) for k in keys if k in sources]
+    src = next((f for f in found if f), None)
+    if not src:
+      continue
+    if part in _DEFAULT_TOWER:
+      cfg_key, default_mod, tower_cfg = _DEFAULT_TOWER[part]
+      mod = importlib.import_module(f"big_vision_b200.models.{model_cfg.get(cfg_key, default_mod)}")
+      result[part] = mod.load(init_params[part], src, model_cfg.get(tower_cfg, {}), **tower_kw[part])
+    else:
+      result[part] = utils.load_params(src)
+  if sources:
+    raise AssertionError(f"Unused entries in `config.model_init` (typo?): {sources}")
+  return result

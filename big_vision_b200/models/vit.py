@@ -23,201 +23,288 @@ from big_vision_b200 import ops
 
 
 def posemb_sincos_2d(h, w, width, temperature=10_000.0):
-  """MoCo v3 layout [sin x, cos x, sin y, cos y] (models/vit.py:34-44). Returns [h*w, width]."""
-  y, x = np.mgrid[:h, :w]
-  assert width % 4 == 0, "Width must be mult of 4 for sincos posemb"
-  omega = np.arange(width // 4) / (width // 4 - 1)
-  omega = 1.0 / (temperature ** omega)
-  y = np.einsum("m,d->md", y.flatten(), omega)
-  x = np.einsum("m,d->md", x.flatten(), omega)
-  pe = np.concatenate([np.sin(x), np.cos(x), np.sin(y), np.cos(y)], axis=1)
-  return pe.astype(np.float32)
+  """Fixed 2-D sine/cosine position table [h*w, width] in the MoCo-v3 channel layout the reference
+  uses (models/vit.py:34-44): the width is cut into four equal bands holding sin(x w_k), cos(x w_k),
+  sin(y w_k), cos(y w_k) for the token at column x, row y (row-major token order), with frequencies
+  w_k = temperature^(-k/(width/4 - 1))."""
+  if width % 4:
+    raise AssertionError("Width must be mult of 4 for sincos posemb")
+  bands = width // 4
+  freq = 1.0 / temperature ** (np.arange(bands) / (bands - 1))
+  col = np.tile(np.arange(w), h)          # x of token t = t % w
+  row = np.repeat(np.arange(h), w)        # y of token t = t // w
+  ax, ay = np.outer(col, freq), np.outer(row, freq)
+  return np.concatenate([np.sin(ax), np.cos(ax), np.sin(ay), np.cos(ay)], axis=1).astype(np.float32)
+
+
+# name: (width, depth, mlp_dim, num_heads) -- the size table of models/vit.py:284-303
+_VARIANTS = {
+    "mu": (32, 1, 128, 2), "Ti": (192, 12, 768, 3), "S": (384, 12, 1536, 6), "M": (512, 12, 2048, 8),
+    "B": (768, 12, 3072, 12), "L": (1024, 24, 4096, 16), "So400m": (1152, 27, 4304, 16),
+    "H": (1280, 32, 5120, 16), "g": (1408, 40, 6144, 16), "g-opt": (1536, 40, 6144, 16),
+    "G": (1664, 48, 8192, 16), "G-opt": (1536, 48, 8192, 16), "e": (1792, 56, 15360, 16),
+}
 
 
 def decode_variant(variant):
-  """Converts a string like "B" or "B/32" into a params dict (models/vit.py:284-303)."""
+  """"B" / "B/16" -> dict(width, depth, mlp_dim, num_heads[, patch_size]); None -> {}."""
   if variant is None:
     return {}
-  v, patch = variant, {}
-  if "/" in variant:
-    v, patch = variant.split("/")
-    patch = {"patch_size": (int(patch), int(patch))}
-  return {
-      "width": {"mu": 32, "Ti": 192, "S": 384, "M": 512, "B": 768, "L": 1024, "So400m": 1152, "H": 1280, "g": 1408, "g-opt": 1536, "G": 1664, "G-opt": 1536, "e": 1792}[v],
-      "depth": {"mu": 1, "Ti": 12, "S": 12, "M": 12, "B": 12, "L": 24, "So400m": 27, "H": 32, "g": 40, "g-opt": 40, "G": 48, "G-opt": 48, "e": 56}[v],
-      "mlp_dim": {"mu": 128, "Ti": 768, "S": 1536, "M": 2048, "B": 3072, "L": 4096, "So400m": 4304, "H": 5120, "g": 6144, "g-opt": 6144, "G": 8192, "G-opt": 8192, "e": 15360}[v],
-      "num_heads": {"mu": 2, "Ti": 3, "S": 6, "M": 8, "B": 12, "L": 16, "So400m": 16, "H": 16, "g": 16, "g-opt": 16, "G": 16, "G-opt": 16, "e": 16}[v],
-      **patch
-  }
+  name, _, patch = variant.partition("/")
+  width, depth, mlp_dim, num_heads = _VARIANTS[name]
+  out = dict(width=width, depth=depth, mlp_dim=mlp_dim, num_heads=num_heads)
+  if patch:
+    out["patch_size"] = (int(patch), int(patch))
+  return out
 
 
 # ------------------------------------------------------------------------------------------
 # building blocks (each: specs(), fwd(), bwd()); `P` is an engine.FlatParams
 # ------------------------------------------------------------------------------------------
-def ln_specs(p, d):
-  return [E.ParamSpec(p + "scale", (d,), E.ones), E.ParamSpec(p + "bias", (d,), E.zeros)]
+def _stacked(init, stack):
+  """Initialiser of a scan-stacked parameter: `stack` independent draws along a new leading axis."""
+  if not stack:
+    return init
+  return lambda rng, shape: np.stack([np.asarray(init(rng, tuple(shape[1:]))) for _ in range(shape[0])])
 
 
-def mlp_specs(p, d, m):
+def _shape(shape, stack):
+  return ((stack,) + tuple(shape)) if stack else tuple(shape)
+
+
+def ln_specs(p, d, stack=0):
+  return [E.ParamSpec(p + "scale", _shape((d,), stack), _stacked(E.ones, stack)),
+          E.ParamSpec(p + "bias", _shape((d,), stack), _stacked(E.zeros, stack))]
+
+
+def mlp_specs(p, d, m, stack=0):
   """MlpBlock (models/vit.py:57-78): xavier_uniform kernels, normal(1e-6) biases."""
   return [
-      E.ParamSpec(p + "Dense_0/kernel", (d, m), E.xavier_uniform(d, m)),
-      E.ParamSpec(p + "Dense_0/bias", (m,), E.normal(1e-6)),
-      E.ParamSpec(p + "Dense_1/kernel", (m, d), E.xavier_uniform(m, d)),
-      E.ParamSpec(p + "Dense_1/bias", (d,), E.normal(1e-6)),
+      E.ParamSpec(p + "Dense_0/kernel", _shape((d, m), stack), _stacked(E.xavier_uniform(d, m), stack)),
+      E.ParamSpec(p + "Dense_0/bias", _shape((m,), stack), _stacked(E.normal(1e-6), stack)),
+      E.ParamSpec(p + "Dense_1/kernel", _shape((m, d), stack), _stacked(E.xavier_uniform(m, d), stack)),
+      E.ParamSpec(p + "Dense_1/bias", _shape((d,), stack), _stacked(E.normal(1e-6), stack)),
   ]
 
 
-def mlp_fwd(P, p, y, resid, out_dtype=torch.bfloat16):
-  """resid + Dense_1(gelu(Dense_0(y))).  Returns (out, saved)."""
-  act, pre = ops.gemm(y, P.h(p + "Dense_0/kernel"), b_mn=True, bias=P.f(p + "Dense_0/bias"),
+class Scope:
+  """A parameter sub-tree of a FlatParams: `S.f("Dense_0/kernel")` is the fp32 master of
+  `prefix + "Dense_0/kernel"` (g: gradient, h: bf16 shadow).  With `index` the stored tensors carry
+  a leading stack axis (the reference's scan=True layout, models/vit.py:129-148: one `encoderblock`
+  sub-tree whose leaves have a leading `depth` axis) and the scope addresses slice `index` of it."""
+
+  def __init__(self, P, prefix, index=None):
+    self.P, self.prefix, self.index = P, prefix, index
+
+  def _get(self, kind, name):
+    full = self.prefix + name
+    if self.index is None:
+      return getattr(self.P, kind)(full)
+    key = (kind, full, self.index)
+    v = self.P._views.get(key)   # pylint: disable=protected-access
+    if v is None:
+      v = getattr(self.P, kind)(full)[self.index]
+      self.P._views[key] = v     # pylint: disable=protected-access
+    return v
+
+  def f(self, name):
+    return self._get("f", name)
+
+  def g(self, name):
+    return self._get("g", name)
+
+  def h(self, name):
+    return self._get("h", name)
+
+  def sub(self, rel):
+    return Scope(self.P, self.prefix + rel, self.index)
+
+
+def mlp_fwd(S, y, resid, out_dtype=torch.bfloat16):
+  """resid + Dense_1(gelu(Dense_0(y))) with S the MlpBlock's Scope.  Returns (out, saved)."""
+  act, pre = ops.gemm(y, S.h("Dense_0/kernel"), b_mn=True, bias=S.f("Dense_0/bias"),
                       epilogue=L.EPI_BIAS_GELU)
-  out = ops.gemm(act, P.h(p + "Dense_1/kernel"), b_mn=True, bias=P.f(p + "Dense_1/bias"),
+  out = ops.gemm(act, S.h("Dense_1/kernel"), b_mn=True, bias=S.f("Dense_1/bias"),
                  aux=resid, epilogue=L.EPI_BIAS_RESID if resid is not None else L.EPI_BIAS,
                  out_dtype=out_dtype)
   return out, (y, act, pre)
 
 
-def mlp_bwd(P, p, dout, saved, want_bias2_grad=True):
+def mlp_bwd(S, dout, saved, want_bias2_grad=True):
   """dout: bf16 [M,d] gradient of the block output.  Returns d(y) (bf16).
 
   The bias gradient of Dense_1 is colsum(dout); callers that already have that column sum
   from the LayerNorm-backward kernel pass want_bias2_grad=False."""
   y, act, pre = saved
   if want_bias2_grad:
-    ops.colsum(dout, P.g(p + "Dense_1/bias"))
-  ops.gemm(act, dout, a_mn=True, b_mn=True, out=P.g(p + "Dense_1/kernel"), reduce_out=True)
+    ops.colsum(dout, S.g("Dense_1/bias"))
+  ops.gemm(act, dout, a_mn=True, b_mn=True, out=S.g("Dense_1/kernel"), reduce_out=True)
   # the Dense_0 bias gradient (column sums of dpre) is accumulated by the same GEMM's epilogue
-  dpre = ops.gemm(dout, P.h(p + "Dense_1/kernel"), aux=pre, epilogue=L.EPI_DGELU,
-                  colsum=P.g(p + "Dense_0/bias"))
-  ops.gemm(y, dpre, a_mn=True, b_mn=True, out=P.g(p + "Dense_0/kernel"), reduce_out=True)
-  return ops.gemm(dpre, P.h(p + "Dense_0/kernel"))
+  dpre = ops.gemm(dout, S.h("Dense_1/kernel"), aux=pre, epilogue=L.EPI_DGELU,
+                  colsum=S.g("Dense_0/bias"))
+  ops.gemm(y, dpre, a_mn=True, b_mn=True, out=S.g("Dense_0/kernel"), reduce_out=True)
+  return ops.gemm(dpre, S.h("Dense_0/kernel"))
 
 
-def mha_specs(p, d, heads, fuse_qkv=True):
+def mha_specs(p, d, heads, fuse_qkv=True, stack=0):
   """flax MultiHeadDotProductAttention params: query/key/value kernels [d,h,dh] + bias [h,dh],
   out kernel [h,dh,d] + bias [d]; kernel_init xavier_uniform (models/vit.py:95,177), zero biases.
-  Stored fused ([d,3d] or q:[d,d] + kv:[d,2d]) and aliased to the reference names."""
+  Stored fused ([d,3d] or q:[d,d] + kv:[d,2d]) and aliased to the reference names.  `stack` > 0
+  adds the leading scan axis to every stored tensor and every alias."""
   dh = d // heads
   xav = E.xavier_uniform(d, d)
+  ax = 1 if stack else 0          # axis of the `d` input features in the stored kernels
 
   def fused_init(k):
-    return lambda rng, shape: np.concatenate([xav(rng, (d, d)) for _ in range(k)], axis=1)
+    return _stacked(lambda rng, shape: np.concatenate([xav(rng, (d, d)) for _ in range(k)], axis=1), stack)
 
   specs, aliases = [], []
 
-  def alias_cols(store, names, width):
+  def alias_cols(store, names):
     for i, nm in enumerate(names):
       aliases.append(E.Alias(p + nm + "/kernel", p + store + "/kernel",
-                             lambda t, i=i: t[:, i * d:(i + 1) * d].unflatten(1, (heads, dh))))
+                             lambda t, i=i: t.narrow(ax + 1, i * d, d).unflatten(ax + 1, (heads, dh))))
       aliases.append(E.Alias(p + nm + "/bias", p + store + "/bias",
-                             lambda t, i=i: t[i * d:(i + 1) * d].unflatten(0, (heads, dh))))
+                             lambda t, i=i: t.narrow(ax, i * d, d).unflatten(ax, (heads, dh))))
 
   if fuse_qkv:
-    specs += [E.ParamSpec(p + "qkv/kernel", (d, 3 * d), fused_init(3)),
-              E.ParamSpec(p + "qkv/bias", (3 * d,), E.zeros)]
-    alias_cols("qkv", ["query", "key", "value"], 3 * d)
+    specs += [E.ParamSpec(p + "qkv/kernel", _shape((d, 3 * d), stack), fused_init(3)),
+              E.ParamSpec(p + "qkv/bias", _shape((3 * d,), stack), _stacked(E.zeros, stack))]
+    alias_cols("qkv", ["query", "key", "value"])
   else:
-    specs += [E.ParamSpec(p + "q/kernel", (d, d), xav), E.ParamSpec(p + "q/bias", (d,), E.zeros),
-              E.ParamSpec(p + "kv/kernel", (d, 2 * d), fused_init(2)),
-              E.ParamSpec(p + "kv/bias", (2 * d,), E.zeros)]
-    alias_cols("q", ["query"], d)
-    alias_cols("kv", ["key", "value"], 2 * d)
-  specs += [E.ParamSpec(p + "out_proj/kernel", (d, d), xav), E.ParamSpec(p + "out/bias", (d,), E.zeros)]
+    specs += [E.ParamSpec(p + "q/kernel", _shape((d, d), stack), _stacked(xav, stack)),
+              E.ParamSpec(p + "q/bias", _shape((d,), stack), _stacked(E.zeros, stack)),
+              E.ParamSpec(p + "kv/kernel", _shape((d, 2 * d), stack), fused_init(2)),
+              E.ParamSpec(p + "kv/bias", _shape((2 * d,), stack), _stacked(E.zeros, stack))]
+    alias_cols("q", ["query"])
+    alias_cols("kv", ["key", "value"])
+  specs += [E.ParamSpec(p + "out_proj/kernel", _shape((d, d), stack), _stacked(xav, stack)),
+            E.ParamSpec(p + "out/bias", _shape((d,), stack), _stacked(E.zeros, stack))]
   aliases.append(E.Alias(p + "out/kernel", p + "out_proj/kernel",
-                         lambda t: t.unflatten(0, (heads, dh))))
+                         lambda t: t.unflatten(ax, (heads, dh))))
   return specs, aliases
 
 
 class EncoderBlock:
-  """Encoder1DBlock (models/vit.py:81-112): x + MHSA(LN(x)); x + MLP(LN(x))."""
+  """Encoder1DBlock (models/vit.py:81-112): x + MHSA(LN(x)); x + MLP(LN(x)).
+  `index` = position in the scan-stacked `encoderblock` sub-tree (None: own `encoderblock_{i}`)."""
 
-  def __init__(self, prefix, d, m, heads):
-    self.p, self.d, self.m, self.heads = prefix, d, m, heads
-    self.att = prefix + "MultiHeadDotProductAttention_0/"
+  def __init__(self, prefix, d, m, heads, index=None):
+    self.p, self.d, self.m, self.heads, self.index = prefix, d, m, heads, index
 
-  def specs(self):
-    s, a = mha_specs(self.att, self.d, self.heads)
-    return (ln_specs(self.p + "LayerNorm_0/", self.d) + s + ln_specs(self.p + "LayerNorm_1/", self.d)
-            + mlp_specs(self.p + "MlpBlock_0/", self.d, self.m)), a
+  def specs(self, stack=0):
+    att = self.p + "MultiHeadDotProductAttention_0/"
+    s, a = mha_specs(att, self.d, self.heads, stack=stack)
+    return (ln_specs(self.p + "LayerNorm_0/", self.d, stack) + s + ln_specs(self.p + "LayerNorm_1/", self.d, stack)
+            + mlp_specs(self.p + "MlpBlock_0/", self.d, self.m, stack)), a
+
+  def scope(self, P):
+    return Scope(P, self.p, self.index)
 
   def fwd(self, P, x, n, N):
-    p, d = self.p, self.d
-    ln1, mean1, rstd1 = ops.layernorm_fwd(x, P.f(p + "LayerNorm_0/scale"), P.f(p + "LayerNorm_0/bias"))
-    qkv = ops.gemm(ln1, P.h(self.att + "qkv/kernel"), b_mn=True, bias=P.f(self.att + "qkv/bias"))
+    d = self.d
+    S = self.scope(P)
+    A = S.sub("MultiHeadDotProductAttention_0/")
+    ln1, mean1, rstd1 = ops.layernorm_fwd(x, S.f("LayerNorm_0/scale"), S.f("LayerNorm_0/bias"))
+    qkv = ops.gemm(ln1, A.h("qkv/kernel"), b_mn=True, bias=A.f("qkv/bias"))
     qkv3 = qkv.view(n, N, 3 * d)
     o, lse = ops.attention_fwd(qkv3[:, :, 0:d], qkv3[:, :, d:2 * d], qkv3[:, :, 2 * d:], self.heads)
-    x1 = ops.gemm(o.view(n * N, d), P.h(self.att + "out_proj/kernel"), b_mn=True,
-                  bias=P.f(self.att + "out/bias"), aux=x, epilogue=L.EPI_BIAS_RESID)
-    ln2, mean2, rstd2 = ops.layernorm_fwd(x1, P.f(p + "LayerNorm_1/scale"), P.f(p + "LayerNorm_1/bias"))
-    x2, mlp_saved = mlp_fwd(P, p + "MlpBlock_0/", ln2, x1)
+    x1 = ops.gemm(o.view(n * N, d), A.h("out_proj/kernel"), b_mn=True,
+                  bias=A.f("out/bias"), aux=x, epilogue=L.EPI_BIAS_RESID)
+    ln2, mean2, rstd2 = ops.layernorm_fwd(x1, S.f("LayerNorm_1/scale"), S.f("LayerNorm_1/bias"))
+    x2, mlp_saved = mlp_fwd(S.sub("MlpBlock_0/"), ln2, x1)
     return x2, (x, ln1, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, mlp_saved)
+
+  def dense1_bias_grad(self, P):
+    """Receives colsum(d block-output): the gradient of this block's MlpBlock Dense_1 bias."""
+    return self.scope(P).g("MlpBlock_0/Dense_1/bias")
 
   def bwd(self, P, dx2, saved, n, N, dx_colsum_out):
     """dx2: bf16 [M,d] grad of block output; colsum(dx2) has ALREADY been accumulated into
     this block's Dense_1 bias grad by whoever produced dx2.  Returns dx (grad of block input);
     colsum(dx) is accumulated into `dx_colsum_out` (the upstream bias/posemb gradient)."""
-    p, d = self.p, self.d
+    d = self.d
+    S = self.scope(P)
+    A = S.sub("MultiHeadDotProductAttention_0/")
     x, ln1, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, mlp_saved = saved
-    dln2 = mlp_bwd(P, p + "MlpBlock_0/", dx2, mlp_saved, want_bias2_grad=False)
-    dx1 = ops.layernorm_bwd(dln2, x1, P.f(p + "LayerNorm_1/scale"), mean2, rstd2, dres=dx2,
-                            dscale=P.g(p + "LayerNorm_1/scale"), dbias=P.g(p + "LayerNorm_1/bias"),
-                            dx_colsum=P.g(self.att + "out/bias"))
+    dln2 = mlp_bwd(S.sub("MlpBlock_0/"), dx2, mlp_saved, want_bias2_grad=False)
+    dx1 = ops.layernorm_bwd(dln2, x1, S.f("LayerNorm_1/scale"), mean2, rstd2, dres=dx2,
+                            dscale=S.g("LayerNorm_1/scale"), dbias=S.g("LayerNorm_1/bias"),
+                            dx_colsum=A.g("out/bias"))
     del dln2
     o2 = o.view(n * N, d)
-    ops.gemm(o2, dx1, a_mn=True, b_mn=True, out=P.g(self.att + "out_proj/kernel"), reduce_out=True)
-    do = ops.gemm(dx1, P.h(self.att + "out_proj/kernel"))
+    ops.gemm(o2, dx1, a_mn=True, b_mn=True, out=A.g("out_proj/kernel"), reduce_out=True)
+    do = ops.gemm(dx1, A.h("out_proj/kernel"))
     qkv3 = qkv.view(n, N, 3 * d)
     dqkv = torch.empty_like(qkv)
     dqkv3 = dqkv.view(n, N, 3 * d)
-    gb = P.g(self.att + "qkv/bias")     # q|k|v bias gradients come out of the attention backward
+    gb = A.g("qkv/bias")     # q|k|v bias gradients come out of the attention backward
     ops.attention_bwd(do.view(n, N, d), qkv3[:, :, 0:d], qkv3[:, :, d:2 * d], qkv3[:, :, 2 * d:],
                       o, lse, self.heads, dq=dqkv3[:, :, 0:d], dk=dqkv3[:, :, d:2 * d],
                       dv=dqkv3[:, :, 2 * d:], dq_colsum=gb[0:d], dk_colsum=gb[d:2 * d],
                       dv_colsum=gb[2 * d:])
     del do
-    ops.gemm(ln1, dqkv, a_mn=True, b_mn=True, out=P.g(self.att + "qkv/kernel"), reduce_out=True)
-    dln1 = ops.gemm(dqkv, P.h(self.att + "qkv/kernel"))
+    ops.gemm(ln1, dqkv, a_mn=True, b_mn=True, out=A.g("qkv/kernel"), reduce_out=True)
+    dln1 = ops.gemm(dqkv, A.h("qkv/kernel"))
     del dqkv
-    dx = ops.layernorm_bwd(dln1, x, P.f(p + "LayerNorm_0/scale"), mean1, rstd1, dres=dx1,
-                           dscale=P.g(p + "LayerNorm_0/scale"), dbias=P.g(p + "LayerNorm_0/bias"),
+    dx = ops.layernorm_bwd(dln1, x, S.f("LayerNorm_0/scale"), mean1, rstd1, dres=dx1,
+                           dscale=S.g("LayerNorm_0/scale"), dbias=S.g("LayerNorm_0/bias"),
                            dx_colsum=dx_colsum_out)
     return dx
 
 
 class Encoder:
   """vit.Encoder (models/vit.py:115-160): depth blocks + LayerNorm("encoder_norm").
-  Python loop over blocks (the reference's scan=False path); param names encoderblock_{i}."""
 
-  def __init__(self, prefix, depth, d, m, heads):
-    self.prefix, self.depth, self.d = prefix, depth, d
-    self.blocks = [EncoderBlock(f"{prefix}encoderblock_{i}/", d, m, heads) for i in range(depth)]
+  scan=False: a Python loop over `encoderblock_{i}` (models/vit.py:151-158); everything the backward
+  needs is kept.  scan=True: the reference's nn.scan over ONE `encoderblock` whose parameters carry
+  a leading depth axis, each iteration wrapped in nn.remat with policy `nothing_saveable`
+  (models/vit.py:129-148): only the block INPUT survives the forward and the block is recomputed
+  in the backward, which is what makes L/14@336 at 2048 pairs per GPU fit in HBM."""
+
+  def __init__(self, prefix, depth, d, m, heads, scan=False, remat_policy="nothing_saveable"):
+    self.prefix, self.depth, self.d, self.scan = prefix, depth, d, scan
+    if scan and remat_policy not in ("nothing_saveable", None):
+      raise NotImplementedError(f"remat_policy={remat_policy!r}: only nothing_saveable (recompute the "
+                                "whole block) is built")
+    if scan:
+      self.blocks = [EncoderBlock(f"{prefix}encoderblock/", d, m, heads, index=i) for i in range(depth)]
+    else:
+      self.blocks = [EncoderBlock(f"{prefix}encoderblock_{i}/", d, m, heads) for i in range(depth)]
 
   def specs(self):
     specs, aliases = [], []
-    for b in self.blocks:
-      s, a = b.specs()
-      specs += s
-      aliases += a
-    specs += ln_specs(self.prefix + "encoder_norm/", self.d)
+    if self.scan:
+      specs, aliases = self.blocks[0].specs(stack=self.depth)
+    else:
+      for b in self.blocks:
+        s, a = b.specs()
+        specs += s
+        aliases += a
+    specs = specs + ln_specs(self.prefix + "encoder_norm/", self.d)
     return specs, aliases
 
   def fwd(self, P, x, n, N):
     saved = []
     for b in self.blocks:
+      x_in = x
       x, s = b.fwd(P, x, n, N)
-      saved.append(s)
+      saved.append(x_in if self.scan else s)      # remat: keep the block input only
     return x, saved   # pre-encoder_norm activations; the caller applies encoder_norm
 
   def last_bias_grad(self, P):
     """Gradient buffer that must receive colsum(d x_out): the last block's Dense_1 bias."""
-    return P.g(self.blocks[-1].p + "MlpBlock_0/Dense_1/bias")
+    return self.blocks[-1].dense1_bias_grad(P)
 
   def bwd(self, P, dx, saved, n, N, dx_colsum_out):
     for i in reversed(range(self.depth)):
-      cs = (P.g(self.blocks[i - 1].p + "MlpBlock_0/Dense_1/bias") if i > 0 else dx_colsum_out)
-      dx = self.blocks[i].bwd(P, dx, saved[i], n, N, cs)
-      saved[i] = None
+      cs = self.blocks[i - 1].dense1_bias_grad(P) if i > 0 else dx_colsum_out
+      s = saved[i]
+      if self.scan:                               # recompute the block from its input
+        x_out, s = self.blocks[i].fwd(P, s, n, N)
+        del x_out
+      dx = self.blocks[i].bwd(P, dx, s, n, N, cs)
+      saved[i] = s = None
     return dx
 
 
@@ -245,7 +332,7 @@ class MAPHead:
     o, lse = ops.attention_fwd(qn.view(n, 1, d), kv3[:, :, 0:d], kv3[:, :, d:], self.heads)
     a = ops.gemm(o.view(n, d), P.h(self.att + "out_proj/kernel"), b_mn=True, bias=P.f(self.att + "out/bias"))
     y, mean, rstd = ops.layernorm_fwd(a, P.f(self.p + "LayerNorm_0/scale"), P.f(self.p + "LayerNorm_0/bias"))
-    out, mlp_saved = mlp_fwd(P, self.p + "MlpBlock_0/", y, a, out_dtype=torch.float32)
+    out, mlp_saved = mlp_fwd(Scope(P, self.p + "MlpBlock_0/"), y, a, out_dtype=torch.float32)
     return out, (enc, qn, kv, o, lse, a, mean, rstd, mlp_saved)
 
   def bwd(self, P, dout, saved, n, N):
@@ -253,7 +340,7 @@ class MAPHead:
     d = self.d
     enc, qn, kv, o, lse, a, mean, rstd, mlp_saved = saved
     dout16 = ops.cast(dout, torch.empty_like(dout, dtype=torch.bfloat16))
-    dy = mlp_bwd(P, self.p + "MlpBlock_0/", dout16, mlp_saved, want_bias2_grad=True)
+    dy = mlp_bwd(Scope(P, self.p + "MlpBlock_0/"), dout16, mlp_saved, want_bias2_grad=True)
     da = ops.layernorm_bwd(dy, a, P.f(self.p + "LayerNorm_0/scale"), mean, rstd, dres=dout16,
                            dscale=P.g(self.p + "LayerNorm_0/scale"), dbias=P.g(self.p + "LayerNorm_0/bias"),
                            dx_colsum=P.g(self.att + "out/bias"))
@@ -308,7 +395,8 @@ class _Model:
       raise NotImplementedError("the attention kernels are built for head dim 64")
     self.mlp = self.mlp_dim or 4 * self.width
     self.prefix = (self.name + "/") if self.name else ""
-    self.encoder = Encoder(self.prefix + "Transformer/", self.depth, self.width, self.mlp, self.num_heads)
+    self.encoder = Encoder(self.prefix + "Transformer/", self.depth, self.width, self.mlp, self.num_heads,
+                           scan=self.scan, remat_policy=self.remat_policy)
     self.map_head = (MAPHead(self.prefix + "MAPHead_0/", self.width, self.mlp, self.num_heads)
                      if self.pool_type == "map" else None)
     self._geom = None
@@ -494,91 +582,127 @@ def Model(num_classes=None, *, variant=None, **kw):  # pylint: disable=invalid-n
 
 
 # ----------------------------------------------------------------------------------------------
-# Checkpoint loading (host side; nested dicts of numpy arrays under the reference's names).
-# Mirrors models/vit.py:306-433.
+# Checkpoint interchange (host side; nested dicts of numpy arrays under the reference's names).
+# Contract of models/vit.py:306-433: accept every on-disk generation of ViT checkpoints the
+# reference accepts and deliver a tree shaped like the model's freshly initialised parameters.
 # ----------------------------------------------------------------------------------------------
 def resample_posemb(old, new):
-  """'High-res finetuning': bilinear (order-1 spline) rescale of the [1, N, d] grid of position
-  embeddings to the shape of `new` -- models/vit.py:306-322."""
-  import scipy.ndimage
+  """Position embeddings for a different input resolution ("high-res finetuning"): the square
+  [1, g*g, d] grid `old` is bilinearly resized (order-1 spline, scipy.ndimage.zoom) to the grid size
+  of `new`; returned unchanged when the shapes already agree."""
   old = np.asarray(old)
-  if old.shape == tuple(new.shape):
+  want = tuple(new.shape)
+  if old.shape == want:
     return old
-  gs_old = int(np.sqrt(old.shape[1]))
-  gs_new = int(np.sqrt(new.shape[1]))
-  grid = old.reshape(gs_old, gs_old, -1)
-  zoom = (gs_new / gs_old, gs_new / gs_old, 1)
-  grid = scipy.ndimage.zoom(grid, zoom, order=1)
-  return grid.reshape(1, gs_new * gs_new, -1)
+  import scipy.ndimage
+  side_from, side_to = (int(np.sqrt(shape[1])) for shape in (old.shape, want))
+  ratio = side_to / side_from
+  resized = scipy.ndimage.zoom(old.reshape(side_from, side_from, -1), (ratio, ratio, 1), order=1)
+  return resized.reshape(1, side_to * side_to, -1)
+
+
+# Older checkpoint generations, oldest quirk first; each entry rewrites the top-level tree in place.
+def _posemb_out_of_encoder(tree):
+  """The position embedding used to be a parameter of the encoder ("Transformer/pos_embedding", and
+  before that of a "posembed_input" sub-module); today it is a top-level parameter."""
+  enc = tree.get("Transformer")
+  if not isinstance(enc, dict):
+    return
+  enc = tree["Transformer"] = dict(enc)
+  if "posembed_input" in enc:
+    tree["pos_embedding"] = enc.pop("posembed_input")["pos_embedding"]
+  if "pos_embedding" in enc:
+    tree["pos_embedding"] = enc.pop("pos_embedding")
+
+
+def _cls_out_of_posemb(tree):
+  """[cls] used to be concatenated BEFORE the position embedding was added, so old tables have
+  g*g + 1 rows; the extra first row is folded into the cls parameter."""
+  table = tree.get("pos_embedding")
+  if table is None:
+    return
+  rows = int(table.shape[1])
+  grid = int(np.sqrt(rows))
+  if grid * grid + 1 != rows:
+    return
+  tree["pos_embedding"] = table[:, 1:]
+  if "cls" in tree:
+    tree["cls"] = tree["cls"] + table[:, :1]
+
+
+def _map_head_into_module(tree):
+  """The MAP head was written inline at first; its four parameter groups now live in "MAPHead_0"."""
+  if "probe" not in tree:
+    return
+  moved = ("probe", "MlpBlock_0", "MultiHeadDotProductAttention_0", "LayerNorm_0")
+  tree["MAPHead_0"] = {name: tree.pop(name) for name in moved}
+
+
+_CHECKPOINT_FIXES = (_posemb_out_of_encoder, _cls_out_of_posemb, _map_head_into_module)
 
 
 def fix_old_checkpoints(params):
-  """Small backward incompatibilities of old ViT checkpoints -- models/vit.py:325-365 (the
-  pre-linen conversion of the reference is not applicable to .npz trees written by linen code)."""
-  params = {k: (dict(v) if isinstance(v, dict) else v) for k, v in params.items()}
-  t = params.get("Transformer", {})
-  if "posembed_input" in t:                       # original ViT paper variant: posemb in a module
-    params["pos_embedding"] = t.pop("posembed_input")["pos_embedding"]
-  if "pos_embedding" in t:                        # pre-2022: posemb inside the Encoder
-    params["pos_embedding"] = t.pop("pos_embedding")
-  if "pos_embedding" in params:                   # old: [cls] concatenated before adding posemb
-    pe = params["pos_embedding"]
-    if int(np.sqrt(pe.shape[1])) ** 2 + 1 == int(pe.shape[1]):
-      pe_cls, params["pos_embedding"] = pe[:, :1], pe[:, 1:]
-      if "cls" in params:
-        params["cls"] = params["cls"] + pe_cls
-  if "probe" in params:                           # MAP head inlined during ViT-G development
-    params["MAPHead_0"] = {k: params.pop(k) for k in
-                           ["probe", "MlpBlock_0", "MultiHeadDotProductAttention_0", "LayerNorm_0"]}
-  return params
+  """Brings a ViT parameter tree of any older generation to today's layout (a new top-level dict;
+  the input is not modified).  Pre-linen checkpoints cannot occur in .npz files written by
+  linen-era code and are not handled."""
+  tree = dict(params)
+  for fix in _CHECKPOINT_FIXES:
+    fix(tree)
+  return tree
 
 
-def _map_leaves(fn, *trees):
-  if isinstance(trees[0], dict):
-    return {k: _map_leaves(fn, *[t[k] for t in trees]) for k in trees[0]}
-  return fn(*trees)
+def _block_names(encoder_tree):
+  names = [k for k in encoder_tree if k.startswith("encoderblock_")]
+  return sorted(names, key=lambda k: int(k.rsplit("_", 1)[1]))
+
+
+def _zip_trees(fn, trees):
+  """fn over corresponding leaves of identically shaped dict trees."""
+  first = trees[0]
+  if isinstance(first, dict):
+    return {k: _zip_trees(fn, [t[k] for t in trees]) for k in first}
+  return fn(trees)
 
 
 def pyloop_to_scan(params_pyloop, encoder="Transformer"):
-  """encoderblock_{i} sub-trees -> one 'encoderblock' with a leading depth axis -- vit.py:368-390."""
-  params = dict(params_pyloop)
-  t = dict(params[encoder])
-  blocks = {k for k in t if k.startswith("encoderblock_")}
-  depth = 1 + max(int(k.split("_")[-1]) for k in blocks)
-  t["encoderblock"] = _map_leaves(lambda *v: np.stack(v), *[t[f"encoderblock_{i}"] for i in range(depth)])
-  for i in range(depth):
-    del t[f"encoderblock_{i}"]
-  params[encoder] = t
-  return params
+  """Per-layer sub-trees "encoderblock_0..L-1" of the Python-loop encoder -> the single
+  "encoderblock" of the scanned encoder, every leaf stacked along a new leading layer axis."""
+  out = dict(params_pyloop)
+  enc = dict(out[encoder])
+  layers = _block_names(enc)
+  if [int(k.rsplit("_", 1)[1]) for k in layers] != list(range(len(layers))):
+    raise ValueError(f"encoder blocks are not numbered 0..{len(layers) - 1}: {layers}")
+  enc["encoderblock"] = _zip_trees(np.stack, [enc.pop(k) for k in layers])
+  out[encoder] = enc
+  return out
 
 
 def scan_to_pyloop(params_scan, encoder="Transformer"):
-  """The inverse of pyloop_to_scan -- vit.py:393-409."""
-  params = dict(params_scan)
-  t = dict(params[encoder])
-  depth = len(t["encoderblock"]["LayerNorm_0"]["bias"])
-  for i in range(depth):
-    t[f"encoderblock_{i}"] = _map_leaves(lambda x, i=i: x[i], t["encoderblock"])
-  del t["encoderblock"]
-  params[encoder] = t
-  return params
+  """The inverse: slice l of every stacked leaf becomes layer "encoderblock_l"."""
+  out = dict(params_scan)
+  enc = dict(out[encoder])
+  stacked = enc.pop("encoderblock")
+  depth = len(stacked["LayerNorm_0"]["bias"])
+  for layer in range(depth):
+    enc[f"encoderblock_{layer}"] = _zip_trees(lambda leaves, layer=layer: leaves[0][layer], [stacked])
+  out[encoder] = enc
+  return out
 
 
 def load(init_params, init_file, model_cfg, dont_load=()):
-  """Init from a checkpoint, old formats included, + hi-res posemb -- models/vit.py:412-433.
-  `init_params` / the result are nested dicts under the reference names (use
-  `utils.recover_tree(*zip(*P.numpy_tree().items()))` and `P.load_tree(dict(flatten))` to go from
-  and to a FlatParams).  This implementation runs the blocks as a Python loop (`scan=False`)."""
+  """Parameters for `model_cfg` initialised from checkpoint `init_file` ("path.npz[:sub/tree]"):
+  older layouts are modernised, the encoder is (un)stacked to match `model_cfg["scan"]`, names
+  matching `dont_load` keep their fresh value from `init_params`, and the position embedding is
+  resampled when the checkpoint was trained at another resolution.  Trees are nested dicts under the
+  reference names (`utils.recover_tree(*zip(*P.numpy_tree().items()))` / `P.load_tree(dict(flat))`
+  convert from and to a FlatParams)."""
   from big_vision_b200 import utils
   from big_vision_b200.models import common
-  restored = utils.load_params(init_file)
-  restored = fix_old_checkpoints(restored)
-  if model_cfg.get("scan") and "encoderblock" not in restored["Transformer"]:
-    restored = pyloop_to_scan(restored)
-  if not model_cfg.get("scan") and "encoderblock" in restored["Transformer"]:
-    restored = scan_to_pyloop(restored)
-  restored = common.merge_params(restored, init_params, dont_load)
+  tree = fix_old_checkpoints(utils.load_params(init_file))
+  stored_scanned = "encoderblock" in tree["Transformer"]
+  if bool(model_cfg.get("scan")) != stored_scanned:
+    tree = scan_to_pyloop(tree) if stored_scanned else pyloop_to_scan(tree)
+  tree = common.merge_params(tree, init_params, dont_load)
   if init_params and "pos_embedding" in init_params:
-    restored["pos_embedding"] = resample_posemb(old=restored["pos_embedding"],
-                                                new=init_params["pos_embedding"])
-  return restored
+    tree["pos_embedding"] = resample_posemb(old=tree["pos_embedding"], new=init_params["pos_embedding"])
+  return tree

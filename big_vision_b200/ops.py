@@ -289,6 +289,15 @@ def untranspose_add(y, res, n, N, d):
   return out
 
 
+def row_select(a, b, mask, n, N):
+  """out[b,t,:] = mask[b] != 0 ? a[b,t,:] : (b[b,t,:] or 0): the stochastic-depth residual gate."""
+  d = a.shape[-1]
+  assert a.dtype == torch.bfloat16 and a.is_contiguous() and mask.dtype == torch.float32
+  out = torch.empty_like(a)
+  L.call("bv_row_select", _p(a), _p(b), _p(mask), _p(out), n, N, d, _stream())
+  return out
+
+
 def concat_cls(x, cls, n, N0):
   d = x.shape[-1]
   out = torch.empty((n * (N0 + 1), d), dtype=torch.bfloat16, device=x.device)
@@ -306,22 +315,26 @@ def drop_cls(x, n, N0):
 def siglip_loss(dots, row_offset, t_param, b_param, global_b, loss, dt, db):
   n, B = dots.shape
   G = torch.empty((n, B), dtype=torch.bfloat16, device=dots.device)
+  # per-block partials + fixed-order finishing pass: the scalars are run-to-run deterministic
+  ws = torch.empty(L.LOSS_WS_FLOATS, dtype=torch.float32, device=dots.device)
   L.call("bv_siglip_loss", _p(dots), n, B, dots.stride(0), row_offset, _p(t_param), _p(b_param),
-         global_b, _p(G), G.stride(0), _p(loss), _p(dt), _p(db), _stream())
+         global_b, _p(G), G.stride(0), _p(loss), _p(dt), _p(db), _p(ws), _stream())
   return G
 
 
 def sigmoid_xent(logits, labels, loss, want_grad=True):
   n, C = logits.shape
   dl = torch.empty_like(logits) if want_grad else None
-  L.call("bv_sigmoid_xent", _p(logits), _p(labels), _p(loss), _p(dl), n, C, _stream())
+  ws = torch.empty(n, dtype=torch.float32, device=logits.device)
+  L.call("bv_sigmoid_xent", _p(logits), _p(labels), _p(loss), _p(dl), _p(ws), n, C, _stream())
   return dl
 
 
 def softmax_xent(logits, labels, loss, want_grad=True):
   n, C = logits.shape
   dl = torch.empty_like(logits) if want_grad else None
-  L.call("bv_softmax_xent", _p(logits), _p(labels), _p(loss), _p(dl), n, C, _stream())
+  ws = torch.empty(n, dtype=torch.float32, device=logits.device)
+  L.call("bv_softmax_xent", _p(logits), _p(labels), _p(loss), _p(dl), _p(ws), n, C, _stream())
   return dl
 
 

@@ -15,13 +15,13 @@ from big_vision_b200.trainers.proj.image_text.siglip import Dist
 _LOSSES = {"sigmoid_xent": ops.sigmoid_xent, "softmax_xent": ops.softmax_xent}
 
 
-def loss_and_grads(model, P, images, labels, loss_name="sigmoid_xent"):
+def loss_and_grads(model, P, images, labels, loss_name="sigmoid_xent", **fwd_kw):
   """value_and_grad(loss_fn)(params) of train.py:295-303 on this rank's shard; P.grad holds the
   LOCAL gradient of the LOCAL-mean loss (callers average across ranks)."""
   if loss_name not in _LOSSES:
     raise NotImplementedError(f"loss {loss_name}")
   P.zero_grad()
-  logits, saved = model.fwd(P, images)
+  logits, saved = model.fwd(P, images, **fwd_kw)
   loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
   dlogits = _LOSSES[loss_name](logits, labels, loss)
   model.bwd(P, dlogits, saved)
@@ -41,7 +41,10 @@ def make_update_fn(model, tx, config):
       if rng is None:
         raise ValueError("mixup needs an rng (numpy Generator)")
       rng, (images, labels), _ = u.get_mixup(rng, mixup_p)(images, labels)
-    loss, _ = loss_and_grads(model, P, images, labels, loss_name)
+    # stochastic depth (Mixer, mlp_mixer.py:173-177) draws its masks from the step's rng like the
+    # reference's `rngs={"dropout": rng}` (train.py:296-299)
+    kw = dict(train=True, rng=rng) if getattr(model, "stoch_depth", 0.0) else {}
+    loss, _ = loss_and_grads(model, P, images, labels, loss_name, **kw)
     # the loss is the mean over the GLOBAL batch: sum the per-rank means and divide by world
     d.all_reduce_sum(P.grad)
     d.all_reduce_sum(loss)

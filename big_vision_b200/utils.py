@@ -1,219 +1,257 @@
-"""Host-side utilities mirrored from big_vision/utils.py that the update step needs:
-`steps` (utils.py:1002-1067, reduced to the keys used here) and
-`create_learning_rate_schedule` (utils.py:1070-1143).  Pure Python/NumPy (runs on the host
-once per step, like the reference's `sched_fns_cpu`)."""
+"""Host-side helpers of the update step and of checkpoint interchange, written against the
+CONTRACT of big_vision/utils.py (behaviour pinned by the reference's own known-answer tests,
+utils_test.py:228-281 for durations / schedules, and by the on-disk .npz format), not against its text:
+
+  steps(prefix, config, ...)               duration keys -> optimizer steps      (utils.py:1002-1067)
+  create_learning_rate_schedule(...)       step -> multiplier                    (utils.py:1070-1143)
+  tree_flatten_with_names / tree_get / recover_tree / load_params / save_checkpoint_np
+                                           flat "a/b/c" names <-> nested trees   (utils.py:133-228,616-752,827-862)
+
+Pure Python / NumPy; runs on the host (the reference evaluates its schedules on the host too,
+`sched_fns_cpu`).
+"""
 import math
+import os
 
 import numpy as np
 
+# ----------------------------------------------------------------------------------------------
+# durations and schedules
+# ----------------------------------------------------------------------------------------------
+_DURATION_UNITS = ("steps", "examples", "epochs", "percent")
+
+
+def _whole_steps(x):
+  """Nearest whole number of steps, but never round a non-zero duration down to nothing."""
+  return max(1, round(x)) if x else 0
+
 
 def steps(prefix, config, data_size=None, batch_size=None, total_steps=None, default=ValueError):
-  """Gets duration named `prefix` out of `config` and converts it to steps (utils.py:1002-1067):
-  `{prefix}_{steps,examples,epochs,percent}`, negative entries ignored, rounded to nearest
-  with a floor of one step unless zero was asked for."""
-  suffixes = ("steps", "examples", "epochs", "percent")
-  matches = set()
-  for s in suffixes:
-    x = config.get(f"{prefix}_{s}")
-    if x is not None and x >= 0:
-      matches.add(f"{prefix}_{s}")
-  assert len(matches) <= 1, f"Only one of '{matches}' should be defined."
+  """Duration `prefix` of `config` in optimizer steps.
 
-  if f"{prefix}_steps" in matches:
-    return config[f"{prefix}_steps"]
-
-  def to_integer(x):
-    return max(1, round(x)) if x else 0
-
-  if batch_size and f"{prefix}_examples" in matches:
-    return to_integer(config[f"{prefix}_examples"] / batch_size)
-  if batch_size and data_size and f"{prefix}_epochs" in matches:
-    return to_integer(config[f"{prefix}_epochs"] * (data_size / batch_size))
-  if total_steps and f"{prefix}_percent" in matches:
-    pct = config[f"{prefix}_percent"]
-    assert 0.0 <= pct <= 1.0, f"Percents should lie in [0.0, 1.0], but {prefix}_percent is {pct}"
-    return to_integer(pct * total_steps)
+  The duration may be given in one of four units, as `{prefix}_steps`, `{prefix}_examples`,
+  `{prefix}_epochs` or `{prefix}_percent` (of `total_steps`); entries that are None or negative count
+  as absent, more than one present is an error.  Conversions need `batch_size` (examples),
+  `batch_size` and `data_size` (epochs) or `total_steps` (percent); when the unit present cannot be
+  converted, or none is present, `default` is returned (raised, if it is ValueError)."""
+  present = {}
+  for unit in _DURATION_UNITS:
+    amount = config.get(f"{prefix}_{unit}")
+    if amount is not None and amount >= 0:
+      present[unit] = amount
+  if len(present) > 1:
+    raise AssertionError(f"Only one of '{ {f'{prefix}_{u}' for u in present} }' should be defined.")
+  if "steps" in present:
+    return present["steps"]
+  if "examples" in present and batch_size:
+    return _whole_steps(present["examples"] / batch_size)
+  if "epochs" in present and batch_size and data_size:
+    return _whole_steps(present["epochs"] * (data_size / batch_size))
+  if "percent" in present and total_steps:
+    pct = present["percent"]
+    if not 0.0 <= pct <= 1.0:
+      raise AssertionError(f"Percents should lie in [0.0, 1.0], but {prefix}_percent is {pct}")
+    return _whole_steps(pct * total_steps)
   if default is ValueError:
     raise ValueError(f"Cannot convert {prefix} to steps, due to missing batch_size ({batch_size}), "
                      f"data_size ({data_size}), total_steps ({total_steps}), or config entry")
   return default
 
 
+class _Schedule:
+  """step -> learning-rate multiplier: base value (optionally scaled with batch_size / 256), one of
+  the decay shapes below over the post-warm-up progress in [0, 1], then linear warm-up from zero and
+  linear cool-down to zero.  Evaluates to a Python float holding a float32 value."""
+
+  def __init__(self, total_steps, batch_size, data_size, base, decay_type, scale_with_batchsize, kw):
+    self.total, self.kw, self.decay_type = total_steps, kw, decay_type
+    self.peak = base * batch_size / 256.0 if scale_with_batchsize else base
+    dur = lambda name, default=0: steps(name, kw, data_size, batch_size, total_steps, default=default)
+    self.warmup, self.cooldown = dur("warmup"), dur("cooldown")
+    if total_steps > 1 and not self.warmup < total_steps:
+      raise AssertionError("warmup_steps is >= total_steps")
+    if decay_type == "rsqrt":
+      self.timescale = dur("timescale", kw.get("timescale", 10_000))
+      self.shift = dur("shift", kw.get("shift", 0))
+    if decay_type not in self._SHAPES:
+      raise ValueError(f"Unknown lr type {decay_type}")
+
+  # each shape: (self, step, progress) -> value before warm-up / cool-down
+  def _poly(self, step, progress):
+    floor = self.kw.get("end", self.kw.get("linear_end", 0))
+    return floor + (self.peak - floor) * (1.0 - progress) ** self.kw.get("power", 1)
+
+  def _cosine(self, step, progress):
+    return self.peak * 0.5 * (1.0 + math.cos(math.pi * progress))
+
+  def _rsqrt(self, step, progress):
+    past = max(step - self.warmup, 0)          # constant until the warm-up is over
+    return self.peak / math.sqrt(1 + (past + self.shift) / self.timescale)
+
+  def _stair(self, step, progress):
+    boundaries = self.kw.get("steps", [])
+    passed = sum(1 for b in boundaries if b <= step)   # boundaries reached so far (sorted input)
+    return self.peak * ([1.0] + list(self.kw.get("mults", [])))[passed]
+
+  _SHAPES = {"linear": _poly, "polynomial": _poly, "cosine": _cosine, "rsqrt": _rsqrt, "stair": _stair}
+
+  def __call__(self, step):
+    span = float(self.total - self.warmup)
+    progress = min(max((step - self.warmup) / span, 0.0), 1.0)
+    value = self._SHAPES[self.decay_type](self, step, progress)
+    if self.warmup:
+      value *= min(1.0, step / self.warmup)
+    if self.cooldown:
+      value *= min(1.0, (self.total - step) / self.cooldown)
+    return float(np.float32(value))
+
+
 def create_learning_rate_schedule(total_steps, batch_size=None, data_size=None, base=1.0,
                                   decay_type="stair", scale_with_batchsize=False, **kw):
-  """Same semantics as utils.py:1070-1143; returns step -> float."""
+  """Schedule factory with the reference's signature; durations in `kw` (`warmup_*`, `cooldown_*`,
+  `timescale_*`, `shift_*`) go through `steps`.  Returns a callable step -> float."""
+  return _Schedule(total_steps, batch_size, data_size, base, decay_type, scale_with_batchsize, kw)
 
-  def to_steps(name, default=0):
-    return steps(name, kw, data_size, batch_size, total_steps, default=default)
 
-  warmup_steps = to_steps("warmup")
-  cooldown_steps = to_steps("cooldown")
-  assert (total_steps <= 1) or (warmup_steps < total_steps), "warmup_steps is >= total_steps"
+# ----------------------------------------------------------------------------------------------
+# Checkpoint interchange: the reference's .npz format.  A checkpoint is a tree (nested dicts; tuples
+# and lists are addressed by position) whose leaves are arrays; on disk every leaf is one .npz entry
+# named by its path joined with "/", and the entries appear in sorted-key order.
+# ----------------------------------------------------------------------------------------------
+def _children(node):
+  """(key as str, child) pairs of an inner node in canonical order, or None for a leaf."""
+  if isinstance(node, dict):
+    return [(k, node[k]) for k in sorted(node)]
+  if isinstance(node, (list, tuple)):
+    return [(str(i), c) for i, c in enumerate(node)]
+  return None
 
-  def step_fn(step):
-    lr = base
-    if scale_with_batchsize:
-      lr = lr * batch_size / 256.0
-    progress = (step - warmup_steps) / float(total_steps - warmup_steps)
-    progress = float(np.clip(progress, 0.0, 1.0))
-    if decay_type in ("linear", "polynomial"):
-      power = kw.get("power", 1)
-      zero = kw.get("end", kw.get("linear_end", 0))
-      lr = zero + (lr - zero) * (1.0 - progress) ** power
-    elif decay_type == "cosine":
-      lr = lr * 0.5 * (1.0 + math.cos(math.pi * progress))
-    elif decay_type == "rsqrt":
-      t = to_steps("timescale", default=kw.get("timescale", 10_000))
-      shift = to_steps("shift", default=kw.get("shift", 0))
-      if warmup_steps <= step:
-        lr = lr / math.sqrt(1 + (step + shift - warmup_steps) / t)
-      else:
-        lr = lr / math.sqrt(1 + shift / t)
-    elif decay_type == "stair":
-      i = int(np.searchsorted(np.array(kw.get("steps", [])), step + 1))
-      lr = lr * ([1.0] + list(kw.get("mults", [])))[i]
+
+def _walk(tree, inner=False):
+  """Depth-first (path, node) pairs; leaves always, inner nodes too when `inner` (after their
+  children, the root under the empty path).  None sub-trees are empty."""
+  stack = [("", tree, False)]
+  while stack:
+    path, node, expanded = stack.pop()
+    if node is None:
+      continue
+    kids = _children(node)
+    if kids is None:
+      yield path, node
+    elif expanded:
+      yield path, node
     else:
-      raise ValueError(f"Unknown lr type {decay_type}")
-    if warmup_steps:
-      lr = lr * min(1.0, step / warmup_steps)
-    if cooldown_steps:
-      lr = lr * min(1.0, (total_steps - step) / cooldown_steps)
-    return float(np.float32(lr))
-
-  return step_fn
-
-
-# ----------------------------------------------------------------------------------------------
-# Checkpoint interchange: the reference's .npz format (flat "a/b/c" keys), SURVEY 8f rank 3.
-# Trees are nested dicts (tuples / lists by index) of numpy arrays; everything here is host code.
-# ----------------------------------------------------------------------------------------------
-import collections as _collections
-import os as _os
-import re as _re
-
-
-def _traverse_with_names(tree, with_inner_nodes=False):
-  """(name, leaf) pairs in sorted-key order -- utils.py:616-640."""
-  if tree is None:
-    return
-  if isinstance(tree, dict):
-    for key in sorted(tree.keys()):
-      for path, v in _traverse_with_names(tree[key], with_inner_nodes):
-        yield (key + "/" + path).rstrip("/"), v
-    if with_inner_nodes:
-      yield "", tree
-  elif isinstance(tree, (list, tuple)):
-    for idx in range(len(tree)):
-      for path, v in _traverse_with_names(tree[idx], with_inner_nodes):
-        yield (str(idx) + "/" + path).rstrip("/"), v
-    if with_inner_nodes:
-      yield "", tree
-  else:
-    yield "", tree
+      if inner:
+        stack.append((path, node, True))
+      for key, child in reversed(kids):
+        stack.append((f"{path}/{key}" if path else key, child, False))
 
 
 def tree_flatten_with_names(tree):
-  """[(name, value), ...] -- utils.py:642-670 for dict / tuple / list trees (for those, jax's
-  flattening order is the sorted-key order produced here).  Returns (names_and_vals, None)."""
-  return list(_traverse_with_names(tree)), None
+  """([(name, leaf), ...], None): the leaves in canonical order with their "a/b/c" names (for trees
+  of dicts / tuples / lists this is also jax's flattening order, so positions line up with
+  jax.tree.leaves on the reference side)."""
+  return list(_walk(tree)), None
 
 
 def tree_get(tree, name):
-  """Entry of a tree by flattened key, e.g. 'a/b/c' or an inner node 'a/b' -- utils.py:726-752."""
-  flattened = dict(_traverse_with_names(tree, with_inner_nodes=True))
-  try:
-    return flattened[name]
-  except KeyError:
-    raise KeyError("\n".join([name, "Available keys:", *flattened, ""])) from None
+  """The leaf -- or whole sub-tree -- stored under the flat name `name`."""
+  node = tree
+  for part in (name.split("/") if name else []):
+    kids = _children(node)
+    nxt = dict(kids).get(part, None) if kids is not None else None
+    if nxt is None and not (kids is not None and part in dict(kids)):
+      known = [p for p, _ in _walk(tree, inner=True)]
+      raise KeyError("\n".join([name, "Available keys:", *known, ""]))
+    node = nxt
+  return node
 
 
 def recover_tree(keys, values):
-  """Nested dict from flat '/'-separated names -- utils.py:836-862."""
-  tree = {}
-  sub_trees = _collections.defaultdict(list)
-  for k, v in zip(keys, values):
-    if "/" not in k:
-      tree[k] = v
-    else:
-      k_left, k_right = k.split("/", 1)
-      sub_trees[k_left].append((k_right, v))
-  for k, kv_pairs in sub_trees.items():
-    k_subtree, v_subtree = zip(*kv_pairs)
-    tree[k] = recover_tree(k_subtree, v_subtree)
-  return tree
+  """Inverse of the flattening for dict trees: {"a/b": 1, "a/c": 2, "d": 3} -> {"a": {"b": 1, "c": 2},
+  "d": 3}.  Key order of the result follows first appearance."""
+  root = {}
+  for name, value in zip(keys, values):
+    *parents, leaf = name.split("/")
+    node = root
+    for part in parents:
+      node = node.setdefault(part, {})
+    node[leaf] = value
+  return root
 
 
 def recover_dtype(a):
-  """numpy stores bfloat16 as a 2-byte void type (utils.py:827-833); there is no numpy bfloat16
-  here, so such arrays come back as float32 (exact: bf16 is the top half of fp32)."""
-  if hasattr(a, "dtype") and a.dtype.type is np.void:
-    assert a.itemsize == 2, "Unknown dtype!"
+  """numpy has no bfloat16: a bf16 array round-trips through .npz as 2-byte void records.  Such
+  leaves are widened to float32 here (exact -- bf16 is the top half of an fp32 word)."""
+  if getattr(a, "dtype", None) is not None and a.dtype.kind == "V":
+    if a.itemsize != 2:
+      raise AssertionError("Unknown dtype!")
     return (a.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
   return a
 
 
 def npload(fname):
-  """np.ndarray (np.save file) or dict of arrays (np.savez file) -- utils.py:133-149."""
-  loaded = np.load(fname, allow_pickle=False)
-  return loaded if isinstance(loaded, np.ndarray) else dict(loaded)
+  """An array (.npy) or a dict of arrays (.npz)."""
+  data = np.load(fname, allow_pickle=False)
+  return data if isinstance(data, np.ndarray) else {k: data[k] for k in data.files}
 
 
 def load_checkpoint_np(npz):
-  """Nested tree from a .npz path or dict-like of flat names -- utils.py:152-170."""
-  if isinstance(npz, str):
-    npz = npload(npz)
-  keys, values = zip(*list(npz.items()))
-  return recover_tree(keys, values)
+  """Tree of a .npz checkpoint given by path or as an already-loaded mapping of flat names."""
+  flat = npload(npz) if isinstance(npz, str) else npz
+  names = list(flat.keys())
+  return recover_tree(names, [flat[k] for k in names])
 
 
 def _tree_map(fn, tree):
+  kids = _children(tree)
+  if kids is None:
+    return fn(tree)
   if isinstance(tree, dict):
-    return {k: _tree_map(fn, v) for k, v in tree.items()}
-  if isinstance(tree, (list, tuple)):
-    return type(tree)(_tree_map(fn, v) for v in tree)
-  return fn(tree)
+    return {k: _tree_map(fn, tree[k]) for k in tree}
+  return type(tree)(_tree_map(fn, c) for c in tree)
 
 
 def load_params(ckpt):
-  """Parameters of a big_vision .npz checkpoint -- utils.py:173-228 (npz branch).  `ckpt` may be
-  '/path/file.npz:img/head' to take a sub-tree, or an already-loaded dict-like.  Handles the three
-  containers the reference does: {'params': ...}, {'opt': {'target': ...}}, or the bare tree."""
-  key = None
+  """Model parameters out of a checkpoint.  `ckpt`: an already-loaded mapping, or a path
+  "dir/file.npz" optionally followed by ":sub/tree" to select part of the parameters.  The parameters
+  sit under "params" (train-state checkpoints), under "opt/target" (older optimizer-state
+  checkpoints) or are the whole file (bare parameter dumps)."""
+  subtree = None
   if isinstance(ckpt, str):
-    match = _re.match(r"^(.*?/.*?)(?::([\w/]+))?$", ckpt)
-    if not match:
+    path, sep, rest = ckpt.rpartition(":")
+    if sep and "/" in path and all(ch.isalnum() or ch in "_/" for ch in rest) and rest:
+      ckpt, subtree = path, rest
+    if "/" not in ckpt:
       raise ValueError(f"Weird ckpt path: {ckpt} ; Maybe prepend ./ ?")
-    ckpt, key = match.groups()
     if ".npz" not in ckpt:
       raise ValueError("only the .npz checkpoint format is supported here")
-  checkpoint = _tree_map(recover_dtype, load_checkpoint_np(ckpt))
-  if "params" in checkpoint:
-    params = checkpoint["params"]
-  elif "opt" in checkpoint:
-    params = checkpoint["opt"]["target"]
-  else:
-    params = checkpoint
-  if key is not None:
-    params = tree_get(params, key)
-  return params
+  tree = _tree_map(recover_dtype, load_checkpoint_np(ckpt))
+  if "params" in tree:
+    tree = tree["params"]
+  elif "opt" in tree:
+    tree = tree["opt"]["target"]
+  return tree if subtree is None else tree_get(tree, subtree)
 
 
 def save_checkpoint_np(checkpoint, path):
-  """Writes a tree as the reference's .npz: one array per leaf under its flat name, atomically
-  (temporary file + rename), like the reference's npz writer."""
-  names_and_vals, _ = tree_flatten_with_names(checkpoint)
+  """Writes a tree in the reference's .npz layout (one entry per leaf, flat names), via a temporary
+  file and a rename so that a reader never sees a half-written checkpoint."""
+  entries = {name: np.asarray(leaf) for name, leaf in _walk(checkpoint)}
   tmp = path + "-TEMPORARY.npz"
   with open(tmp, "wb") as f:
-    np.savez(f, **{k: np.asarray(v) for k, v in names_and_vals})
-  _os.replace(tmp, path)
+    np.savez(f, **entries)
+  os.replace(tmp, path)
 
 
 def check_and_compile_patterns(patterns):
-  """utils.py: a str or a sequence of regex strs -> compiled patterns."""
+  """One regex string or a sequence of them -> list of compiled patterns."""
+  import re
   if isinstance(patterns, str):
     patterns = [patterns]
-  assert isinstance(patterns, (list, tuple)), patterns
-  return [_re.compile(p) for p in patterns]
+  if not isinstance(patterns, (list, tuple)):
+    raise AssertionError(f"Must be a sequence of regex strings: {patterns!r}")
+  return [re.compile(p) for p in patterns]
 
 
 # ----------------------------------------------------------------------------------------------

@@ -172,6 +172,12 @@ int bv_transpose_tokens(const void* x, void* y, int64_t n, int32_t N, int32_t d,
 int bv_untranspose_add(const void* y, const void* res, void* out, int64_t n, int32_t N, int32_t d,
                        void* stream);
 
+/* Stochastic-depth residual gate (models/mlp_mixer.py:52,55 with the per-sample mask of :173-177,
+ * mask = 1 - Bernoulli(drop_p), no 1/(1-p) rescale): out[b,t,:] = mask[b] != 0 ? a[b,t,:] :
+ * (b ? b[b,t,:] : 0).  a, b, out bf16 [n,N,d]; mask fp32 [n]; b may be NULL (backward: mask * dout). */
+int bv_row_select(const void* a, const void* b, const float* mask, void* out, int64_t n, int32_t N,
+                  int32_t d, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Losses
  * --------------------------------------------------------------------------------- */
@@ -179,15 +185,21 @@ int bv_untranspose_add(const void* y, const void* res, void* out, int64_t n, int
  * (trainers/proj/image_text/siglip.py:291-306; per-device form
  * _deprecated_contrastive.py:117-141).  row_offset = rank*n locates the positives.
  * Accumulates: loss += sum_ij -loglik_ij / global_B ; dt += dloss/dt' ; db += dloss/db.
- * Writes G[n,B] (bf16) = dloss/ddots. */
+ * Writes G[n,B] (bf16) = dloss/ddots.
+ * partials_ws: NULL = the three scalars are accumulated with one atomicAdd per block (order of
+ * arrival, last-bit differences between runs); a workspace of BV_LOSS_WS_FLOATS floats = per-block
+ * partials + a fixed-order finishing pass, i.e. run-to-run deterministic like the reference. */
+#define BV_LOSS_WS_FLOATS 8192
 int bv_siglip_loss(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
                    const float* t_param, const float* b_param, int64_t global_B, void* G,
-                   int64_t ldg, float* loss, float* dt, float* db, void* stream);
-/* utils.py:236-243 / 276-281 : mean over n rows; loss is accumulated; dlogits may be NULL */
+                   int64_t ldg, float* loss, float* dt, float* db, float* partials_ws,
+                   void* stream);
+/* utils.py:236-243 / 276-281 : mean over n rows; loss is accumulated; dlogits may be NULL.
+ * row_loss_ws: NULL = atomics; [n] floats = per-row losses + fixed-order sum (deterministic). */
 int bv_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                    int64_t n, int32_t C, void* stream);
+                    float* row_loss_ws, int64_t n, int32_t C, void* stream);
 int bv_softmax_xent(const float* logits, const float* labels, float* loss, float* dlogits,
-                    int64_t n, int32_t C, void* stream);
+                    float* row_loss_ws, int64_t n, int32_t C, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Optimizer (optax.py:143-149 chain with scale_by_adam; siglip.py:312-321)

@@ -260,8 +260,10 @@ def softmax_xent(logits, labels):
   return (-(labels * torch.log_softmax(logits, -1)).sum(-1)).mean()
 
 
-def mixer_forward(p, image, cfg, mm="float32"):
-  """mlp_mixer.MlpMixer.__call__ (models/mlp_mixer.py:70-84), stoch_depth = 0."""
+def mixer_forward(p, image, cfg, mm="float32", masks=None):
+  """mlp_mixer.MlpMixer.__call__ (models/mlp_mixer.py:70-84).  `masks` [num_blocks, 2, n] are the
+  per-sample stochastic-depth masks 1 - Bernoulli(drop_p) of mlp_mixer.py:173-177 (None = all ones,
+  i.e. stoch_depth = 0 or eval mode); the residual adds are `x + y * mask` (:52,:55), no rescale."""
   image = image.to(F64)
   x = rnd(patch_embed(image, p["stem/kernel"], p["stem/bias"], mm), mm)
   for i in range(cfg["num_blocks"]):
@@ -271,11 +273,16 @@ def mixer_forward(p, image, cfg, mm="float32"):
     tm = sub(bp, "token_mixing/")
     h = rnd(gelu_tanh(rnd(dense(y, tm["Dense_0/kernel"], tm["Dense_0/bias"], mm), mm)), mm)
     y = rnd(dense(h, tm["Dense_1/kernel"], tm["Dense_1/bias"], mm), mm).transpose(1, 2)
+    if masks is not None:
+      y = y * torch.as_tensor(masks[i][0]).to(F64)[:, None, None]
     x = rnd(x + y, mm)
     y = rnd(layer_norm(x, bp["LayerNorm_1/scale"], bp["LayerNorm_1/bias"]), mm)
     cm = sub(bp, "channel_mixing/")
     h = rnd(gelu_tanh(rnd(dense(y, cm["Dense_0/kernel"], cm["Dense_0/bias"], mm), mm)), mm)
-    x = rnd(x + rnd(dense(h, cm["Dense_1/kernel"], cm["Dense_1/bias"], mm), mm), mm)
+    y = rnd(dense(h, cm["Dense_1/kernel"], cm["Dense_1/bias"], mm), mm)
+    if masks is not None:
+      y = y * torch.as_tensor(masks[i][1]).to(F64)[:, None, None]
+    x = rnd(x + y, mm)
   x = layer_norm(x, p["pre_head_layer_norm/scale"], p["pre_head_layer_norm/bias"])
   x = x.mean(1)
   if cfg.get("num_classes"):

@@ -19,10 +19,10 @@ from big_vision_b200.models import vit
 def test_tree_helpers_known_answers():
   d1 = {"w1": 1, "w2": 2, "w34": (3, 4)}
   d2 = {"conv1": {"kernel": 0, "bias": 1}, "conv2": {"kernel": 2, "bias": 3}}
-  assert list(u._traverse_with_names(d1)) == [("w1", 1), ("w2", 2), ("w34/0", 3), ("w34/1", 4)]
-  assert list(u._traverse_with_names(d2)) == [("conv1/bias", 1), ("conv1/kernel", 0),
+  assert list(u._walk(d1)) == [("w1", 1), ("w2", 2), ("w34/0", 3), ("w34/1", 4)]
+  assert list(u._walk(d2)) == [("conv1/bias", 1), ("conv1/kernel", 0),
                                               ("conv2/bias", 3), ("conv2/kernel", 2)]
-  assert list(u._traverse_with_names(d2, with_inner_nodes=True)) == [
+  assert list(u._walk(d2, inner=True)) == [
       ("conv1/bias", 1), ("conv1/kernel", 0), ("conv1", d2["conv1"]),
       ("conv2/bias", 3), ("conv2/kernel", 2), ("conv2", d2["conv2"]), ("", d2)]
   assert u.tree_flatten_with_names(d1)[0] == [("w1", 1), ("w2", 2), ("w34/0", 3), ("w34/1", 4)]
