@@ -134,14 +134,17 @@ class ClockSampler:
             "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_batch(wl, n, seed):
+def synthetic_batch(wl, n, seed, uint8=False):
   """SURVEY.md 8d synthetic inputs: images U(-1,1) fp32 NHWC; text ids U{2..31999} for a random length
   then sticky EOS/pad id 1; class labels one-hot fp32 [n, 1000].  Returns dict of numpy arrays."""
   import numpy as np
   rng = np.random.default_rng(seed)
   res = wl["res"]
   # uniform fp32 in [-1, 1): generated in float32 directly (2.8 GB at config 5 would be 5.5 GB in f64)
-  image = rng.random(size=(n, res, res, 3), dtype=np.float32) * np.float32(2) - np.float32(1)
+  if uint8:      # decoded pixels; value_range(-1, 1) is applied on the device (bv_patchify_u8)
+    image = rng.integers(0, 256, size=(n, res, res, 3), dtype=np.uint8)
+  else:
+    image = rng.random(size=(n, res, res, 3), dtype=np.float32) * np.float32(2) - np.float32(1)
   if wl["kind"] == "siglip":
     text = np.ones((n, TXT_LEN), dtype=np.int32)
     lens = rng.integers(4, TXT_LEN, size=n)
@@ -402,7 +405,7 @@ def measure_ours(args, wl, world, rank, local_rank):
   else:
     from big_vision_b200 import train
     update_fn = train.make_update_fn(model, tx, {**OPT_CONFIG, "loss": wl["loss"]})
-  host = synthetic_batch(wl, n, seed=rank)
+  host = synthetic_batch(wl, n, seed=rank, uint8=args.input == "uint8")
   pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
   del host
   batch = {k: v.cuda() for k, v in pinned.items()}
@@ -585,7 +588,7 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}: {wl['desc']}",
                    "global_batch": n * world, "per_gpu_batch": n,
                    "seq_len": seq.get(wl["kind"], (wl["res"] // 16) ** 2),
-                   "parallelism": f"dp{world}",
+                   "parallelism": f"dp{world}", "image_input": args.input,
                    "l2_policy": f"inputs ({R['h2d'] / 1e6:.0f} MB/step) and activations (GBs) exceed the "
                                 "126 MB L2; no explicit flush",
                    "final_loss": R["loss"], "peak_mem_gib": R["peak_mem_gib"]},
@@ -621,6 +624,9 @@ def main():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
   ap.add_argument("--workload", default="siglip_b16", choices=sorted(WORKLOADS))
   ap.add_argument("--per-gpu-batch", type=int, default=0, help="0 = the workload's BASELINE.json shard")
+  ap.add_argument("--input", default="float32", choices=["float32", "uint8"],
+                  help="image hand-off: fp32 in [-1,1] (the reference's) or decoded uint8 with value_range "
+                       "fused into the patch extraction (a quarter of the H2D bytes)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-gpu-baseline", action="store_true")
   ap.add_argument("--profile-calls", action="store_true",

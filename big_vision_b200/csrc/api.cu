@@ -69,7 +69,7 @@ int bv_attention_bwd(const bv_attn_bwd_args* a, void* stream) {
   g.lddq = a->lddq; g.lddk = a->lddk; g.lddv = a->lddv;
   g.bsdq = a->bsdq; g.bsdk = a->bsdk; g.bsdv = a->bsdv;
   g.dq_colsum = a->dq_colsum; g.dk_colsum = a->dk_colsum; g.dv_colsum = a->dv_colsum;
-  g.delta = nullptr;
+  g.delta = a->delta; g.dq_accum = a->dq_accum;
   return launch_attention_bwd(g, S(stream));
 }
 
@@ -81,6 +81,11 @@ int bv_debug_gemm_timeline(long long* host, int n) { return gemm_debug_read(host
 int bv_patchify(const float* image, void* patches, int64_t n, int32_t H, int32_t W, int32_t C,
                 int32_t P, void* stream) {
   return launch_patchify(image, patches, n, H, W, C, P, S(stream));
+}
+int bv_patchify_u8(const uint8_t* image, void* patches, int64_t n, int32_t H, int32_t W, int32_t C,
+                   int32_t P, float vmin, float vmax, float in_min, float in_max, int32_t clip_values,
+                   void* stream) {
+  return launch_patchify_u8(image, patches, n, H, W, C, P, vmin, vmax, in_min, in_max, clip_values, S(stream));
 }
 int bv_embed_fwd(const int32_t* ids, const float* table, const float* pos, void* out,
                  int out_dtype, int64_t n, int32_t L, int32_t d, int32_t vocab, void* stream) {
@@ -177,6 +182,12 @@ int bv_adam_step(const bv_adam_args* a, void* stream) {
   g.grad_scale_host = a->grad_mult; g.gnorm_sq = a->gnorm_sq; g.clip_norm = a->clip_norm;
   g.step = a->step; g.upd_sq = a->upd_sq; g.param_sq = a->param_sq;
   return launch_adam(g, S(stream));
+}
+int bv_scale_step(float* params, const float* grads, void* params_bf16, int64_t n, float lr_eff,
+                  float wd_eff, float grad_mult, float clip_norm, const float* gnorm_sq, float* upd_sq,
+                  float* param_sq, void* stream) {
+  return launch_scale_step(params, grads, params_bf16, n, lr_eff, wd_eff, grad_mult, clip_norm, gnorm_sq,
+                           upd_sq, param_sq, S(stream));
 }
 int bv_sumsq(const float* x, float* out, int64_t n, void* stream) {
   return launch_sumsq(x, out, n, S(stream));

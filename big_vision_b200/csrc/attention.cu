@@ -15,26 +15,14 @@
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"
+#include "attn_common.cuh"
 
 #include <stdlib.h>
 
 namespace bv {
 namespace {
 
-constexpr int DH = 64;
-constexpr int TQ = 128;
-constexpr int TILE_BYTES = TQ * DH * 2;       // 16 KB: 128 rows x 128 B
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7])
-      : "r"(taddr)
-      : "memory");
-}
+using namespace attn;
 
 // ============================================================================
 // forward
@@ -74,33 +62,6 @@ __host__ __device__ inline FwdSmem fwd_smem_layout(int NKP, int nstage) {
   L.total = L.bar_off + 160 + 1024;
   return L;
 }
-
-template <int R> __device__ __forceinline__ void reg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R));
-}
-template <int R> __device__ __forceinline__ void reg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R));
-}
-__device__ __forceinline__ float ex2_mufu(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5,
-// degree-4 polynomial for 2^f (rel. error < 5e-5, far inside the bf16 rounding of P), exponent
-// patched in with integer arithmetic.  B200's MUFU.EX2 sustains ~8 lanes/clk/SM, which makes the
-// exponentials the bound of the softmax; splitting them between MUFU and this path doubles the rate.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.0f);
-  const float t = x + 12582912.0f;     // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float pl = fmaf(f, 0.0096181291f, 0.0555041087f);
-  pl = fmaf(pl, f, 0.2402265070f);
-  pl = fmaf(pl, f, 0.6931471806f);
-  pl = fmaf(pl, f, 1.0f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
-}
-
 
 // Everything the softmax warpgroups need, copied into registers once (kernel parameters live in
 // constant memory; re-reading them inside the unrolled per-unit code costs an LDCU round trip each
@@ -1010,22 +971,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-int make_tmap_bnd(CUtensorMap* m, const void* ptr, int cols, int64_t N, int64_t B, int64_t ld,
-                  int64_t bs, uint32_t box_rows) {
-  uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
-  uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(bs) * 2};
-  uint32_t box[3] = {64, box_rows, 1};
-  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, true);
-}
-
 int check_attn(const AttnArgs& a, const char* who) {
-  if (a.B <= 0 || a.H <= 0 || a.Nq <= 0 || a.Nk <= 0 || a.Nq > 256 || a.Nk > 256) {
-    set_error("%s: need 1 <= Nq,Nk <= 256 and B,H >= 1 (got B=%lld H=%d Nq=%d Nk=%d)", who,
+  if (a.B <= 0 || a.H <= 0 || a.Nq <= 0 || a.Nk <= 0 || a.Nq > 65536 || a.Nk > 65536) {
+    set_error("%s: need 1 <= Nq,Nk <= 65536 and B,H >= 1 (got B=%lld H=%d Nq=%d Nk=%d)", who,
               (long long)a.B, a.H, a.Nq, a.Nk);
     return BV_ERR_INVALID;
   }
-  if (a.B * a.H * 2 > 0x7fffffffLL) { set_error("%s: too many (batch, head) pairs", who); return BV_ERR_INVALID; }
+  if (a.B * a.H * ((a.Nq + TQ - 1) / TQ) > 0x7fffffffLL) {
+    set_error("%s: too many (batch, head, query tile) work units", who);
+    return BV_ERR_INVALID;
+  }
   return BV_OK;
+}
+
+// Which forward kernel: sequences whose scores fit in TMEM (Nk <= 256) can use the whole-key-range
+// kernel of this file; longer ones need the key-block streaming kernel (attention_stream.cu), which
+// also handles the short ones.  BV_ATTN_FWD = "resident" | "stream" forces one for A/B measurements.
+bool use_stream_fwd(const AttnArgs& a) {
+  const char* e = getenv("BV_ATTN_FWD");     // read per call: tests flip it between launches
+  const int mode = (e && e[0] == 'r') ? 1 : (e && e[0] == 's') ? 2 : 0;
+  if (a.Nk > 256) return true;
+  if (mode == 1) return false;
+  if (mode == 2) return true;
+  return false;
 }
 
 }  // namespace
@@ -1052,6 +1020,7 @@ int attn_debug_read(long long* host, int n) {
 int launch_attention_fwd(const AttnArgs& a, cudaStream_t s) {
   int rc = check_attn(a, "bv_attention_fwd");
   if (rc) return rc;
+  if (use_stream_fwd(a)) return launch_attention_fwd_stream(a, s);
   FwdDev p;
   p.dbg = attn_debug_buffer();
   p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
@@ -1084,6 +1053,13 @@ int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
   int rc = check_attn(a, "bv_attention_bwd");
   if (rc) return rc;
   if (a.lse == nullptr) { set_error("bv_attention_bwd: lse required"); return BV_ERR_INVALID; }
+  {
+    // long sequences stream 128-key tiles (attention_stream.cu); BV_ATTN_BWD=stream forces that kernel
+    // for short ones too when its workspaces were passed (A/B measurements, tests)
+    const char* e = getenv("BV_ATTN_BWD");
+    const bool force = e && e[0] == 's' && g.dq_accum != nullptr && g.delta != nullptr;
+    if (a.Nq > 256 || a.Nk > 256 || force) return launch_attention_bwd_stream(g, s);
+  }
   BwdDev p;
   p.BH = static_cast<int>(a.B * a.H);
   p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;

@@ -62,6 +62,48 @@ __global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict_
   }
 }
 
+// uint8 ingest: the same patch extraction straight from the decoded uint8 image, with the input
+// pipeline's `value_range(vmin, vmax, in_min, in_max, clip)` (pp/ops_general.py:32-64) applied on
+// the way -- fp32, every operation rounded separately like the TensorFlow op:
+//   x = (float(u8) - in_min) / (in_max - in_min);  y = vmin + x * (vmax - vmin);  [clip to vmin..vmax]
+// A quarter of the host->device bytes of the fp32 hand-off (input_pipeline.py:316-329 ships the
+// already-converted fp32 image).  One thread per 8 output columns, as above.
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int64_t n,
+                                   int H, int W, int C, int P, int Kp, float vmin, float vrange,
+                                   float in_min, float in_span, int clip, float vmax) {
+  const int gh = H / P, gw = W / P;
+  const int K = P * P * C, PC = P * C;
+  const int groups = Kp / 8;
+  const int64_t total = n * gh * gw * groups;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    const int64_t patch = idx / groups;
+    const int px = static_cast<int>(patch % gw);
+    const int py = static_cast<int>((patch / gw) % gh);
+    const int64_t b = patch / (static_cast<int64_t>(gw) * gh);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      if (k < K) {
+        const int ph = k / PC, o = k % PC;
+        const float x = static_cast<float>(
+            __ldg(img + ((b * H + (py * P + ph)) * static_cast<int64_t>(W) + px * P) * C + o));
+        float y = __fadd_rn(vmin, __fmul_rn(__fdiv_rn(__fsub_rn(x, in_min), in_span), vrange));
+        if (clip) y = fminf(fmaxf(y, vmin), vmax);
+        v[j] = y;
+      } else {
+        v[j] = 0.f;
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
+    q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + patch * Kp + g * 8) = q;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // token embedding: out[b,l,:] = table[ids[b,l],:] + pos[l,:]
 // (models/proj/image_text/text_transformer.py:63-70)
@@ -424,6 +466,24 @@ int launch_patchify(const float* img, void* out, int64_t n, int H, int W, int C,
   patchify_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(img, reinterpret_cast<bf16*>(out),
                                                                 n, H, W, C, P, Kp);
   return check_launch("patchify_kernel");
+}
+
+int launch_patchify_u8(const uint8_t* img, void* out, int64_t n, int H, int W, int C, int P, float vmin,
+                       float vmax, float in_min, float in_max, int clip, cudaStream_t s) {
+  if (n <= 0 || P <= 0 || H % P || W % P || C <= 0 || !(in_max > in_min)) {
+    set_error("bv_patchify_u8: need n > 0, H,W multiples of P, in_max > in_min");
+    return BV_ERR_INVALID;
+  }
+  const int Kp = (P * P * C + 7) / 8 * 8;
+  const int64_t total = n * (H / P) * (W / P) * (Kp / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  // (vmax - vmin) is evaluated in double and rounded once, like the Python constant of the reference
+  const float vrange = static_cast<float>(static_cast<double>(vmax) - static_cast<double>(vmin));
+  patchify_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      img, reinterpret_cast<bf16*>(out), n, H, W, C, P, Kp, vmin, vrange, in_min, in_max - in_min, clip, vmax);
+  return check_cuda(cudaGetLastError(), "patchify_u8_kernel launch");
 }
 
 int launch_embed_fwd(const int32_t* ids, const float* table, const float* pos, void* out,

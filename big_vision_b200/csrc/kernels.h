@@ -39,15 +39,18 @@ struct AttnArgs {
   float scale;
 };
 int launch_attention_fwd(const AttnArgs& a, cudaStream_t s);
+int launch_attention_fwd_stream(const AttnArgs& a, cudaStream_t s);   // attention_stream.cu
 struct AttnBwdArgs {
   AttnArgs f;
   const void* d_o; int64_t lddo, bsdo;
   void* dq; void* dk; void* dv;                  // bf16, same geometry as q/k/v
   float* dq_colsum; float* dk_colsum; float* dv_colsum;   // optional [H*64] fp32 bias gradients
   int64_t lddq, lddk, lddv, bsdq, bsdk, bsdv;
-  float* delta;                                  // workspace [B, H, Nq]
+  float* delta;                                  // workspace [B, H, Nq] fp32   (streaming kernel)
+  float* dq_accum;                               // workspace [B, Nq, H*64] fp32 (streaming kernel)
 };
 int launch_attention_bwd(const AttnBwdArgs& a, cudaStream_t s);
+int launch_attention_bwd_stream(const AttnBwdArgs& a, cudaStream_t s);   // attention_stream.cu
 int gemm_debug_read(long long* host, int n);   // BV_GEMM_DBG=1 timeline of the last GEMM launch
 int attn_debug_read(long long* host, int n);   // BV_ATTN_DBG=1 timeline of the last fwd launch
 
@@ -61,6 +64,8 @@ int launch_retrieval_ranks(const float* dist, int64_t NI, int64_t NT, int64_t ld
 // ---- element-wise / reductions (elementwise.cu)
 int launch_patchify(const float* img, void* out, int64_t n, int H, int W, int C, int P,
                     cudaStream_t s);
+int launch_patchify_u8(const uint8_t* img, void* out, int64_t n, int H, int W, int C, int P, float vmin,
+                       float vmax, float in_min, float in_max, int clip, cudaStream_t s);
 int launch_untranspose_add(const void* y, const void* res, void* out, int64_t n, int N, int d,
                            cudaStream_t s);
 int launch_concat_cls(const void* x, const float* cls, void* out, int64_t n, int N0, int d,
@@ -118,5 +123,8 @@ struct AdamArgs {
 };
 int launch_adam(const AdamArgs& a, cudaStream_t s);
 int launch_sumsq(const float* x, float* out, int64_t n, cudaStream_t s);
+int launch_scale_step(float* params, const float* grads, void* params_bf16, int64_t n, float lr, float wd,
+                      float grad_mult, float clip_norm, const float* gnorm_sq, float* upd_sq,
+                      float* param_sq, cudaStream_t s);
 
 }  // namespace bv

@@ -95,7 +95,7 @@ ln_fwd_kernel(const void* __restrict__ x, int x_dt, const float* __restrict__ sc
 // bias in registers (re-reading them per row costs 4x the L1 traffic of the row itself) and keep
 // the load of the next row in flight while the current one is reduced and written.
 template <int NCH>
-__global__ void __launch_bounds__(LN_THREADS, 2)
+__global__ void __launch_bounds__(LN_THREADS, NCH <= 3 ? 2 : 1)
 ln_fwd_stream_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
                      const float* __restrict__ bias, bf16* __restrict__ y,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int d,
@@ -266,8 +266,9 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_dt, const void* __restrict__ x
 // (DEPTH-1) rows x 4.5 KB are in flight per SM, enough to cover HBM latency.
 // ---------------------------------------------------------------------------
 constexpr int LNP_DEPTH = 3;
-constexpr int LNP_THREADS = 384;        // 12 warps: the kernel is issue-bound, more warps = more IPC
-constexpr int LNP_WARPS = LNP_THREADS / 32;
+// 12 warps up to d = 768 (the kernel is issue-bound, more warps = more IPC); 8 warps for d <= 1024 so
+// that the per-warp rings (DEPTH x 3 arrays x 2 KB) still fit in shared memory
+template <int NCH> struct LnpCfg { static constexpr int WARPS = NCH <= 3 ? 12 : 8; static constexpr int THREADS = WARPS * 32; };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -288,7 +289,7 @@ __device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
 }
 
 template <int NCH, bool HAS_RES>
-__global__ void __launch_bounds__(LNP_THREADS, 1)
+__global__ void __launch_bounds__(LnpCfg<NCH>::THREADS, 1)
 ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    const float* __restrict__ scale, const float* __restrict__ mean_in,
                    const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
@@ -296,6 +297,7 @@ ln_bwd_pipe_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    float* __restrict__ dx_colsum, int64_t rows, int d) {
   extern __shared__ __align__(16) uint8_t smem_ln[];
   constexpr int NARR = HAS_RES ? 3 : 2;
+  constexpr int LNP_THREADS = LnpCfg<NCH>::THREADS, LNP_WARPS = LnpCfg<NCH>::WARPS;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nchunks = d >> 3;
@@ -423,6 +425,7 @@ int launch_ln_bwd_pipe(const void* dy, const void* x, const float* scale, const 
                        const float* rstd, const void* dres, void* dx, float* dscale, float* dbias,
                        float* dx_colsum, int64_t rows, int d, cudaStream_t s) {
   const int narr = dres ? 3 : 2;
+  constexpr int LNP_THREADS = LnpCfg<NCH>::THREADS, LNP_WARPS = LnpCfg<NCH>::WARPS;
   const size_t smem = 3 * static_cast<size_t>(d) * 4 +
                       static_cast<size_t>(LNP_WARPS) * LNP_DEPTH * narr * d * 2;
   int64_t blocks = (rows + LNP_WARPS - 1) / LNP_WARPS;
@@ -465,14 +468,15 @@ int launch_layernorm_fwd(const void* x, int x_dt, const float* scale, const floa
   if (rc) return rc;
   if (rows == 0) return BV_OK;
   const int nch = (d / 8 + 31) / 32;
-  if (x_dt == DT_BF16 && y_dt == DT_BF16 && rows >= 4096 && nch <= 3) {
-    // streaming fast path: two persistent blocks per SM
-    const unsigned pgrid = static_cast<unsigned>(2 * num_sms());
+  if (x_dt == DT_BF16 && y_dt == DT_BF16 && rows >= 4096 && nch <= 4) {
+    // streaming fast path: two persistent blocks per SM (one for d > 768: twice the registers per row)
+    const unsigned pgrid = static_cast<unsigned>((nch <= 3 ? 2 : 1) * num_sms());
     const bf16* xb = reinterpret_cast<const bf16*>(x);
     bf16* yb = reinterpret_cast<bf16*>(y);
     switch (nch) {
       case 1: ln_fwd_stream_kernel<1><<<pgrid, LN_THREADS, 0, s>>>(xb, scale, bias, yb, mean, rstd, rows, d, eps); break;
       case 2: ln_fwd_stream_kernel<2><<<pgrid, LN_THREADS, 0, s>>>(xb, scale, bias, yb, mean, rstd, rows, d, eps); break;
+      case 4: ln_fwd_stream_kernel<4><<<pgrid, LN_THREADS, 0, s>>>(xb, scale, bias, yb, mean, rstd, rows, d, eps); break;
       default: ln_fwd_stream_kernel<3><<<pgrid, LN_THREADS, 0, s>>>(xb, scale, bias, yb, mean, rstd, rows, d, eps); break;
     }
     return check_cuda(cudaGetLastError(), "ln_fwd_stream_kernel launch");
@@ -504,10 +508,11 @@ int launch_layernorm_bwd(const void* dy, int dy_dt, const void* x, int x_dt, con
     // streaming bf16 fast path (cp.async ring); the generic kernel below covers fp32 operands,
     // small problems and widths whose ring does not fit in shared memory
     const size_t ring = 3 * static_cast<size_t>(d) * 4 +
-                        static_cast<size_t>(LNP_WARPS) * LNP_DEPTH * (dres ? 3 : 2) * d * 2;
-    if (dy_dt == DT_BF16 && x_dt == DT_BF16 && dx_dt == DT_BF16 && rows >= 4096 && nch <= 3 &&
+                        static_cast<size_t>(nch <= 3 ? 12 : 8) * LNP_DEPTH * (dres ? 3 : 2) * d * 2;
+    if (dy_dt == DT_BF16 && x_dt == DT_BF16 && dx_dt == DT_BF16 && rows >= 4096 && nch <= 4 &&
         ring <= 220 * 1024) {
       switch (nch) {
+        case 4: return launch_ln_bwd_pipe<4>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
         case 1: return launch_ln_bwd_pipe<1>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
         case 2: return launch_ln_bwd_pipe<2>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);
         default: return launch_ln_bwd_pipe<3>(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, dx_colsum, rows, d, s);

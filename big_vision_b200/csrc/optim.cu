@@ -89,6 +89,36 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, void* __restrict
   }
 }
 
+// optax.scale(step_size) as the inner transform of the same chain (the reference's optimizer tests
+// use it, optax_test.py:103-299; it is plain SGD): p += -(lr * g' + wd * p), g' = clipped gradient.
+__global__ void __launch_bounds__(256)
+scale_step_kernel(float* __restrict__ p, const float* __restrict__ g, bf16* __restrict__ p16, int64_t n,
+                  float lr, float wd, const float* __restrict__ gnorm_sq, float clip_norm,
+                  float grad_mult, float* __restrict__ upd_sq, float* __restrict__ param_sq) {
+  __shared__ float sh[64];
+  float gscale = grad_mult;
+  if (clip_norm > 0.f && gnorm_sq != nullptr) {
+    const float gn = sqrtf(gnorm_sq[0]) * grad_mult;
+    if (!(gn < clip_norm)) gscale *= clip_norm / gn;
+  }
+  float us = 0.f, ps = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float pp = p[i];
+    const float upd = -(lr * (g[i] * gscale) + wd * pp);
+    pp += upd;
+    us += upd * upd;
+    ps += pp * pp;
+    p[i] = pp;
+    if (p16 != nullptr) p16[i] = __float2bfloat16_rn(pp);
+  }
+  block_reduce2(us, ps, sh);
+  if (threadIdx.x == 0) {
+    if (upd_sq) atomicAdd(upd_sq, us);
+    if (param_sq) atomicAdd(param_sq, ps);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
   __shared__ float sh[64];
@@ -129,6 +159,19 @@ int launch_adam(const AdamArgs& a, cudaStream_t s) {
         a.b2, a.eps, a.wd, bc1, bc2, a.gnorm_sq, a.clip_norm, a.grad_scale_host, a.upd_sq, a.param_sq);
   }
   return check_cuda(cudaGetLastError(), "adam_kernel launch");
+}
+
+int launch_scale_step(float* params, const float* grads, void* params_bf16, int64_t n, float lr, float wd,
+                      float grad_mult, float clip_norm, const float* gnorm_sq, float* upd_sq,
+                      float* param_sq, cudaStream_t s) {
+  if (n <= 0) return BV_OK;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  scale_step_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      params, grads, reinterpret_cast<bf16*>(params_bf16), n, lr, wd, gnorm_sq, clip_norm, grad_mult, upd_sq,
+      param_sq);
+  return check_cuda(cudaGetLastError(), "scale_step_kernel launch");
 }
 
 int launch_sumsq(const float* x, float* out, int64_t n, cudaStream_t s) {

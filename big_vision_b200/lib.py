@@ -37,7 +37,8 @@ class AttnBwdArgs(ctypes.Structure):
               ("dq", c_vp), ("dk", c_vp), ("dv", c_vp),
               ("lddq", c_i64), ("lddk", c_i64), ("lddv", c_i64),
               ("bsdq", c_i64), ("bsdk", c_i64), ("bsdv", c_i64),
-              ("dq_colsum", c_vp), ("dk_colsum", c_vp), ("dv_colsum", c_vp)]
+              ("dq_colsum", c_vp), ("dk_colsum", c_vp), ("dv_colsum", c_vp),
+              ("delta", c_vp), ("dq_accum", c_vp)]
 
 
 class AdamArgs(ctypes.Structure):
@@ -57,6 +58,7 @@ SIGNATURES = {
     "bv_attention_fwd": [ctypes.POINTER(AttnArgs), c_vp],
     "bv_attention_bwd": [ctypes.POINTER(AttnBwdArgs), c_vp],
     "bv_patchify": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "bv_patchify_u8": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp],
     "bv_embed_fwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_vp],
     "bv_embed_bwd": [c_vp, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp],
     "bv_colsum": [c_vp, c_i32, c_vp, c_i64, c_i64, c_i64, c_vp],
@@ -82,6 +84,7 @@ SIGNATURES = {
     "bv_softmax_xent": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
     "bv_adam_step": [ctypes.POINTER(AdamArgs), c_vp],
     "bv_sumsq": [c_vp, c_vp, c_i64, c_vp],
+    "bv_scale_step": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp],
     "bv_top1": [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "bv_retrieval_ranks": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp],
     "bv_version": [],

@@ -305,6 +305,11 @@ class Encoder:
         del x_out
       dx = self.blocks[i].bwd(P, dx, s, n, N, cs)
       saved[i] = s = None
+      # every parameter from this block on (in spec order) now has its final gradient: lets a
+      # data-parallel trainer start reducing them while the earlier blocks are still running
+      hook = getattr(P, "on_ready", None)
+      if hook is not None and not self.scan:
+        hook(self.blocks[i].p + "LayerNorm_0/scale")
     return dx
 
 

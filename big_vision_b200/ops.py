@@ -5,6 +5,7 @@ no eager/CPU implementation behind these calls.
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -156,6 +157,12 @@ def attention_bwd(do, q, k, v, o, lse, heads, scale=None, dq=None, dk=None, dv=N
   if dv is None:
     dv = torch.empty(v.shape, dtype=torch.bfloat16, device=q.device)
   f = _attn_args(q, k, v, o, lse, heads, scale)
+  delta = dq_accum = None
+  B, Nq, cols = q.shape
+  if Nq > 256 or k.shape[1] > 256 or os.environ.get("BV_ATTN_BWD", "")[:1] == "s":
+    # workspaces of the key-tile streaming kernel (long sequences)
+    delta = torch.empty((B, heads, Nq), dtype=torch.float32, device=q.device)
+    dq_accum = torch.empty((B, Nq, cols), dtype=torch.float32, device=q.device)
   dop, lddo, bsdo = _attn_view(do)
   dqp, lddq, bsdq = _attn_view(dq)
   dkp, lddk, bsdk = _attn_view(dk)
@@ -164,14 +171,25 @@ def attention_bwd(do, q, k, v, o, lse, heads, scale=None, dq=None, dk=None, dv=N
                        lddq=lddq, lddk=lddk, lddv=lddv, bsdq=bsdq, bsdk=bsdk, bsdv=bsdv,
                        dq_colsum=dq_colsum.data_ptr() if dq_colsum is not None else None,
                        dk_colsum=dk_colsum.data_ptr() if dk_colsum is not None else None,
-                       dv_colsum=dv_colsum.data_ptr() if dv_colsum is not None else None)
+                       dv_colsum=dv_colsum.data_ptr() if dv_colsum is not None else None,
+                       delta=delta.data_ptr() if delta is not None else None,
+                       dq_accum=dq_accum.data_ptr() if dq_accum is not None else None)
   L.call("bv_attention_bwd", ctypes.byref(args), _stream())
   return dq, dk, dv
 
 
-def patchify(image, patch):
+def patchify(image, patch, value_range=(-1.0, 1.0), in_range=(0.0, 255.0), clip_values=False):
+  """image [n,H,W,C]: fp32 (already in its value range) or uint8 (decoded pixels; `value_range(...)`
+  of the input pipeline, pp/ops_general.py:32-64, is applied on the fly)."""
   n, H, W, C = image.shape
-  assert image.dtype == torch.float32 and image.is_contiguous()
+  assert image.is_contiguous()
+  if image.dtype == torch.uint8:
+    kp = (patch * patch * C + 7) // 8 * 8
+    out = torch.empty((n * (H // patch) * (W // patch), kp), dtype=torch.bfloat16, device=image.device)
+    L.call("bv_patchify_u8", _p(image), _p(out), n, H, W, C, patch, float(value_range[0]),
+           float(value_range[1]), float(in_range[0]), float(in_range[1]), int(clip_values), _stream())
+    return out
+  assert image.dtype == torch.float32
   kp = (patch * patch * C + 7) // 8 * 8
   out = torch.empty((n * (H // patch) * (W // patch), kp), dtype=torch.bfloat16, device=image.device)
   L.call("bv_patchify", _p(image), _p(out), n, H, W, C, patch, _stream())
@@ -354,6 +372,12 @@ def adam_step(params, grads, mu, nu, params_bf16, *, lr_eff, b1, b2, eps, wd_eff
       upd_sq=upd_sq.data_ptr() if upd_sq is not None else None,
       param_sq=param_sq.data_ptr() if param_sq is not None else None)
   L.call("bv_adam_step", ctypes.byref(args), _stream())
+
+
+def scale_step(params, grads, params_bf16, *, lr_eff, wd_eff, grad_mult=1.0, clip_norm=0.0, gnorm_sq=None,
+               upd_sq=None, param_sq=None):
+  L.call("bv_scale_step", _p(params), _p(grads), _p(params_bf16), params.numel(), lr_eff, wd_eff, grad_mult,
+         clip_norm, _p(gnorm_sq), _p(upd_sq), _p(param_sq), _stream())
 
 
 # ---- integer evaluation paths -------------------------------------------------------------------

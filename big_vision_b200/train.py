@@ -15,7 +15,7 @@ from big_vision_b200.trainers.proj.image_text.siglip import Dist
 _LOSSES = {"sigmoid_xent": ops.sigmoid_xent, "softmax_xent": ops.softmax_xent}
 
 
-def loss_and_grads(model, P, images, labels, loss_name="sigmoid_xent", **fwd_kw):
+def loss_and_grads(model, P, images, labels, loss_name="sigmoid_xent", dist_view=None, **fwd_kw):
   """value_and_grad(loss_fn)(params) of train.py:295-303 on this rank's shard; P.grad holds the
   LOCAL gradient of the LOCAL-mean loss (callers average across ranks)."""
   if loss_name not in _LOSSES:
@@ -24,7 +24,11 @@ def loss_and_grads(model, P, images, labels, loss_name="sigmoid_xent", **fwd_kw)
   logits, saved = model.fwd(P, images, **fwd_kw)
   loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
   dlogits = _LOSSES[loss_name](logits, labels, loss)
-  model.bwd(P, dlogits, saved)
+  if dist_view is None:
+    model.bwd(P, dlogits, saved)
+  else:      # gradient all-reduce (SUM; callers divide by world) overlapped with the backward
+    from big_vision_b200.trainers.proj.image_text.siglip import all_reduce_grads
+    all_reduce_grads(P, dist_view, lambda: model.bwd(P, dlogits, saved))
   return loss, logits
 
 
@@ -44,9 +48,8 @@ def make_update_fn(model, tx, config):
     # stochastic depth (Mixer, mlp_mixer.py:173-177) draws its masks from the step's rng like the
     # reference's `rngs={"dropout": rng}` (train.py:296-299)
     kw = dict(train=True, rng=rng) if getattr(model, "stoch_depth", 0.0) else {}
-    loss, _ = loss_and_grads(model, P, images, labels, loss_name, **kw)
+    loss, _ = loss_and_grads(model, P, images, labels, loss_name, dist_view=d, **kw)
     # the loss is the mean over the GLOBAL batch: sum the per-rank means and divide by world
-    d.all_reduce_sum(P.grad)
     d.all_reduce_sum(loss)
     sc = tx.update(P, opt, grad_mult=1.0 / d.world)
     measurements = {

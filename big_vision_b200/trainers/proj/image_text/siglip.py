@@ -14,6 +14,7 @@ GPU box, gloo in the CPU tests).  The loss is normalised by the GLOBAL batch B
 (siglip.py:306), so per-rank partial losses/gradients are SUMMED across ranks.
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -77,6 +78,79 @@ class Dist:
     fn()
     e1.record()
     L.PROFILE.append((name, e0, e1, 0.0))
+
+
+class BucketedGradAllReduce:
+  """C3 overlapped with the backward pass (the reference's `lax.pmean` of the gradients,
+  _deprecated_contrastive.py:343, which XLA schedules under the backward as well).
+
+  Gradients complete in the REVERSE of the parameter-spec order (the loss scalars first, then the
+  text tower from its head down to its embedding, then the image tower likewise), and the flat
+  gradient buffer is laid out in spec order inside each of its two groups (decayed kernels | the
+  rest).  So the finished part of each group grows from the group's end towards its start: whenever
+  the backward reports "everything from spec `name` on is done" (`P.on_ready`, called by
+  vit.Encoder.bwd after every block) and at least `bucket_elems` new elements are final, that slice
+  is all-reduced asynchronously -- NCCL's stream waits for the kernels enqueued so far, the main
+  stream carries on with the next block -- and `finish()` reduces what is left and joins.
+  Elementwise SUM over the same values as one big all-reduce: results are identical."""
+
+  def __init__(self, P, d, bucket_elems=8 << 20):
+    self.P, self.d, self.bucket = P, d, bucket_elems
+    idx = {s.name: i for i, s in enumerate(P.specs)}
+    self.idx = idx
+    self.groups = []                       # (lo, hi, [spec index ...], [offset ...]) in layout order
+    for lo, hi in ((0, P.n_decay), (P.n_decay, P.total)):
+      members = sorted((off, idx[name]) for name, (off, _) in P.offsets.items() if lo <= off < hi)
+      self.groups.append((lo, hi, [m[1] for m in members], [m[0] for m in members]))
+    self.front, self.handles = None, []
+
+  def begin(self):
+    self.front = [hi for _, hi, _, _ in self.groups]
+    self.handles = []
+    self.P.on_ready = self.ready
+
+  def _launch(self, lo, hi):
+    if hi > lo:
+      h = dist.all_reduce(self.P.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+      self.handles.append(h)
+
+  def ready(self, name):
+    """Everything at or after storage parameter `name` in spec order has its final gradient."""
+    k = self.idx[name]
+    for gi, (lo, hi, spec_idx, offs) in enumerate(self.groups):
+      # layout order == spec order inside a group: first member whose spec index is >= k
+      import bisect
+      j = bisect.bisect_left(spec_idx, k)
+      new = offs[j] if j < len(offs) else hi
+      if self.front[gi] - new >= self.bucket:
+        self._launch(new, self.front[gi])
+        self.front[gi] = new
+
+  def finish(self):
+    self.P.on_ready = None
+    for gi, (lo, hi, _, _) in enumerate(self.groups):
+      self._launch(lo, self.front[gi])
+      self.front[gi] = lo
+    for h in self.handles:
+      h.wait()                             # the current stream waits for NCCL's
+    self.handles = []
+
+
+def all_reduce_grads(P, d, run_backward):
+  """Runs `run_backward()` with the gradient all-reduce (SUM) overlapped when there are peers."""
+  if d.world == 1:
+    run_backward()
+    return
+  if os.environ.get("BV_GRAD_ALLREDUCE") == "single":     # A/B switch: one all-reduce after the backward
+    run_backward()
+    d.all_reduce_sum(P.grad)
+    return
+  red = BucketedGradAllReduce(P, d)
+  red.begin()
+  try:
+    run_backward()
+  finally:
+    red.finish()
 
 
 def sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal):
@@ -155,8 +229,8 @@ def make_update_fn(model, tx, config=None):
     scal = torch.zeros(4, dtype=torch.float32, device=P.flat.device)
     zimg, ztxt, saved = model.fwd(P, images, labels)
     dzimg, dztxt = loss_fwd_bwd(P, zimg, ztxt, d, scal)
-    model.bwd(P, dzimg, dztxt, saved)
-    d.all_reduce_sum(P.grad)                               # C3 (+ dt, db inside the flat buffer)
+    # C3 (+ dt, db inside the flat buffer), bucketed and overlapped with the backward
+    all_reduce_grads(P, d, lambda: model.bwd(P, dzimg, dztxt, saved))
     d.all_reduce_sum(scal)                                 # C4: loss
     sc = tx.update(P, opt, grad_mult=1.0)
     measurements = {
@@ -179,7 +253,6 @@ def loss_and_grads(model, P, images, labels, loss_fn="sigmoid"):
   scal = torch.zeros(4, dtype=torch.float32, device=P.flat.device)
   zimg, ztxt, saved = model.fwd(P, images, labels)
   dzimg, dztxt = sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal)
-  model.bwd(P, dzimg, dztxt, saved)
-  d.all_reduce_sum(P.grad)
+  all_reduce_grads(P, d, lambda: model.bwd(P, dzimg, dztxt, saved))
   d.all_reduce_sum(scal)
   return scal[0], {"zimg": zimg, "ztxt": ztxt, "dzimg": dzimg, "dztxt": dztxt}

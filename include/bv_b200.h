@@ -96,8 +96,10 @@ int bv_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
                      int32_t d, void* stream);
 
 /* ---------------------------------------------------------------------------------
- * Scaled-dot-product attention, head dim 64, no mask, Nq,Nk <= 256
- * (flax MultiHeadDotProductAttention core: models/vit.py:93-98, :176-178).
+ * Scaled-dot-product attention, head dim 64, no mask, any Nq, Nk >= 1
+ * (flax MultiHeadDotProductAttention core: models/vit.py:93-98, :176-178).  Sequences up to 256
+ * keys run with the whole key range resident on chip; longer ones (config 5: 576) stream 128-key
+ * blocks (online combination of per-block softmax statistics; attention_stream.cu).
  * q/k/v/o are bf16 strided views: element (b, t, h*64 + j) at
  * base + b*bs + t*ld + h*64 + j  (e.g. column slices of the fused QKV GEMM output).
  * lse [B,H,Nq] fp32 = log sum_j exp(scale * q_i.k_j) is saved for the backward.
@@ -118,6 +120,10 @@ typedef struct bv_attn_bwd_args {
   /* optional fp32 [H*64] each: += column sums over the valid rows of dq / dk / dv, i.e. the bias
    * gradients of the projections that produced q / k / v */
   float* dq_colsum; float* dk_colsum; float* dv_colsum;
+  /* workspaces of the key-tile streaming kernel, REQUIRED when Nq > 256 or Nk > 256 (may be NULL
+   * otherwise): delta [B,H,Nq] fp32 = rowsum(O o dO); dq_accum [B,Nq,H*64] fp32, zeroed by the call,
+   * receives the per-key-tile dQ contributions (TMA reduce-add) before the bf16 conversion into dq */
+  float* delta; float* dq_accum;
 } bv_attn_bwd_args;
 int bv_attention_bwd(const bv_attn_bwd_args* args, void* stream);
 
@@ -128,6 +134,14 @@ int bv_attention_bwd(const bv_attn_bwd_args* args, void* stream);
  * (ph,pw,c) = row-major HWIO conv kernel (models/vit.py:212-217). */
 int bv_patchify(const float* image, void* patches, int64_t n, int32_t H, int32_t W, int32_t C,
                 int32_t P, void* stream);
+/* The same patch extraction from the DECODED uint8 image with the input pipeline's value_range op
+ * fused in (pp/ops_general.py:32-64; configs/vit_i1k.py:96 `value_range(-1, 1)`):
+ *   y = vmin + ((float(u8) - in_min) / (in_max - in_min)) * (vmax - vmin), optionally clipped;
+ * fp32, each operation rounded separately (bit-identical to the TensorFlow op), then bf16.  Cuts the
+ * host->device bytes of the image hand-off (input_pipeline.py:316-329) by 4. */
+int bv_patchify_u8(const uint8_t* image, void* patches, int64_t n, int32_t H, int32_t W, int32_t C,
+                   int32_t P, float vmin, float vmax, float in_min, float in_max, int32_t clip_values,
+                   void* stream);
 /* out[b,l,:] = table[ids[b,l],:] + pos[l,:] (text_transformer.py:63-70); pos may be NULL */
 int bv_embed_fwd(const int32_t* ids, const float* table, const float* pos, void* out,
                  int out_dtype, int64_t n, int32_t L, int32_t d, int32_t vocab, void* stream);
@@ -218,6 +232,12 @@ typedef struct bv_adam_args {
 } bv_adam_args;
 int bv_adam_step(const bv_adam_args* args, void* stream);
 int bv_sumsq(const float* x, float* out, int64_t n, void* stream);
+/* The same chain with optax.scale(step_size) as the inner transform (plain SGD; what the reference's
+ * optimizer known-answer tests drive, optax_test.py:103-299): p += -(lr_eff * g' + wd_eff * p) with
+ * g' = g * grad_mult * clip(gnorm); lr_eff already holds schedule * lr * lr_mult * step_size. */
+int bv_scale_step(float* params, const float* grads, void* params_bf16, int64_t n, float lr_eff,
+                  float wd_eff, float grad_mult, float clip_norm, const float* gnorm_sq, float* upd_sq,
+                  float* param_sq, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Integer evaluation paths (bit-exact index arithmetic)

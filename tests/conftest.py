@@ -17,7 +17,7 @@ def pytest_configure(config):
 # the trainers / evaluators / multi-GPU step.  (With `-x` an early failure in a composite test would
 # otherwise hide the kernel evidence behind it.)
 _GPU_ORDER = ["test_kernels_gpu", "test_attention_gpu", "test_model_gpu", "test_precision_gpu",
-              "test_classifier_gpu", "test_eval_paths", "test_input_pipeline", "test_dist_gpu"]
+              "test_optax_gpu", "test_classifier_gpu", "test_eval_paths", "test_input_pipeline", "test_dist_gpu"]
 
 
 def _gpu_usable():

@@ -116,3 +116,64 @@ def test_sharded_sigmoid_loss_equals_global_loss(world, loss_fn):
     errs = ret.get(r)
     assert errs is not None, f"rank {r} returned nothing"
     assert all(v < 2e-5 for v in errs.values()), (r, dict(errs))
+
+
+def _bucket_worker(rank, world, port, ret):
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.join(ROOT, "tests"))
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  import common
+  from big_vision_b200.models.proj.image_text import two_towers
+  from big_vision_b200.trainers.proj.image_text import siglip
+  model = two_towers.Model(**common.TINY)
+  specs, aliases = model.specs(common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE)
+  from big_vision_b200 import engine
+  P = engine.FlatParams(specs, aliases, "cpu")
+  rng = np.random.default_rng(100 + rank)
+  full = torch.from_numpy(rng.standard_normal(P.total).astype(np.float32))
+  expect = full.clone()
+  dist.all_reduce(expect)
+  red = siglip.BucketedGradAllReduce(P, siglip.Dist(), bucket_elems=3000)
+  launched = []
+  orig = red._launch
+  red._launch = lambda lo, hi: (launched.append((lo, hi)), orig(lo, hi))[1]
+  red.begin()
+  # the backward, as far as the reducer can tell: gradients become final in REVERSE spec order and
+  # every encoder block reports once its first parameter (LayerNorm_0/scale) is done
+  for spec in reversed(P.specs):
+    off, shape = P.offsets[spec.name]
+    n = int(np.prod(shape))
+    P.grad[off:off + n] = full[off:off + n]
+    if spec.name.endswith("LayerNorm_0/scale") and "encoderblock" in spec.name:
+      P.on_ready(spec.name)
+  red.finish()
+  # padding between parameters is never written by a backward: compare the parameter slots only
+  ok = True
+  for name, (off, shape) in P.offsets.items():
+    n = int(np.prod(shape))
+    ok &= bool(torch.equal(P.grad[off:off + n], expect[off:off + n]))
+  spans = sorted(launched)
+  ret[rank] = {"ok": ok, "buckets": len(launched),
+               "disjoint": all(a[1] <= b[0] for a, b in zip(spans, spans[1:])),
+               "covered": sum(hi - lo for lo, hi in spans) == P.total}
+  dist.destroy_process_group()
+
+
+def test_bucketed_gradient_all_reduce_equals_one_all_reduce():
+  """BucketedGradAllReduce (C3 overlapped with the backward): slices are launched only once final,
+  are disjoint, cover the whole flat buffer, and the result equals a single all-reduce."""
+  world = 2
+  port = 29300 + os.getpid() % 500
+  ctx = mp.get_context("spawn")
+  ret = ctx.Manager().dict()
+  procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, ret)) for r in range(world)]
+  for p in procs:
+    p.start()
+  for p in procs:
+    p.join(120)
+    assert p.exitcode == 0
+  for r in range(world):
+    res = dict(ret[r])
+    assert res["ok"] and res["disjoint"] and res["covered"], res
+    assert res["buckets"] >= 4, res          # the backward really was overlapped in several slices

@@ -213,6 +213,25 @@ def test_patchify_embed_pool_l2norm(ops):
   assert torch.equal(ops.pool_fwd(xs.cuda(), 4, 10, 1, tok=9).cpu(), xs.reshape(4, 10, 64)[:, 9])
 
 
+@pytest.mark.parametrize("vr,inr,clip", [((-1.0, 1.0), (0.0, 255.0), False), ((-0.5, 0.5), (-256.0, 255.0), True),
+                                         ((0.0, 1.0), (0.0, 255.0), False)])
+def test_patchify_u8_fuses_value_range_bit_exactly(ops, vr, inr, clip):
+  """uint8 ingest: value_range (pp/ops_general.py:32-64; the cases of ops_general_test.py:36-49) in
+  fp32 with every operation rounded separately, then the same patch layout as the fp32 path."""
+  import numpy as np
+  rng = np.random.default_rng(3)
+  u8 = rng.integers(0, 256, size=(3, 32, 48, 3), dtype=np.uint8)
+  f32 = np.float32
+  x = (u8.astype(f32) - f32(inr[0])) / (f32(inr[1]) - f32(inr[0]))
+  ref = f32(vr[0]) + x * f32(vr[1] - vr[0])
+  if clip:
+    ref = np.clip(ref, f32(vr[0]), f32(vr[1]))
+  assert ref.dtype == np.float32 and ref.min() >= vr[0] and ref.max() <= vr[1]
+  want = ops.patchify(torch.from_numpy(ref).cuda(), 16)
+  got = ops.patchify(torch.from_numpy(u8).cuda(), 16, value_range=vr, in_range=inr, clip_values=clip)
+  assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
 @pytest.mark.parametrize("n,B,off", [(8, 8, 0), (64, 256, 128), (16, 64, 48)])
 def test_siglip_loss_slab(ops, n, B, off):
   """One rank's [n, B] slab of the global loss (positives at column off + i)."""

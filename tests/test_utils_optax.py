@@ -1,6 +1,11 @@
 """CPU: host logic pinned by the reference's own known-answer tables
 (big_vision/utils_test.py:228-281)."""
+import os
+import sys
+
 import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from big_vision_b200 import optax as bv_optax
 from big_vision_b200 import utils as u
@@ -43,14 +48,55 @@ def test_schedule(decay_type, extra, step, expected):          # utils_test.py:2
   assert lr_fn(step) == pytest.approx(expected, abs=1e-6)
 
 
+def _tiny_params():
+  import common
+  from big_vision_b200.models.proj.image_text import two_towers
+  model = two_towers.Model(**common.TINY)
+  return model.init(0, common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, device="cpu")
+
+
 def test_make_rejects_unbuilt_configurations():
+  P = _tiny_params()
   with pytest.raises(NotImplementedError):
-    bv_optax.make(dict(optax_name="big_vision.scale_by_adafactor", schedule={}), None,
+    bv_optax.make(dict(optax_name="big_vision.scale_by_adafactor", schedule={}), P,
                   sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
   tx, fns = bv_optax.make(dict(optax_name="scale_by_adam", optax=dict(b2=0.95), lr=1e-3, wd=1e-4,
                                grad_clip_norm=1.0, schedule=dict(decay_type="cosine", warmup_steps=2)),
-                          None, sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
+                          P, sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
   assert tx.b2 == 0.95 and tx.clip == 1.0 and fns[0](0) == 0.0 and fns[0](2) == pytest.approx(1.0)
+  # default config: two launches -- the decayed kernels (stored first) and everything else
+  assert [(r[0], r[1], r[2], r[4] > 0) for r in tx.ranges] == [(0, P.n_decay, 0, True), (P.n_decay, P.total, 0, False)]
+  assert tx.n_state == P.total
+
+
+def test_make_assigns_first_matching_pattern_and_merges_ranges():
+  """optax.py:79-145 with utils.make_mask_trees (first match wins): frozen image tower
+  (configs/proj/image_text/siglip_lit_coco.py:102 style), lr multiplier on the text head, custom
+  weight-decay multipliers; adjacent parameters with the same setting share a launch."""
+  P = _tiny_params()
+  config = dict(optax_name="scale_by_adam", lr=1e-3, wd=1e-4, lr_mults=[("txt/head/.*", 2.0)],
+                wd_mults=[(".*/kernel", 1.0), ("txt/Embed_0/embedding", 0.5)],
+                schedule=[("img/.*", None), (".*", dict(decay_type="cosine", warmup_steps=2))])
+  tx, fns = bv_optax.make(config, P, sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
+  assert len(fns) == 1
+  names_of = {}
+  for a in P.aliases.values():
+    names_of.setdefault(a.storage, []).append(a.name)
+  covered = 0
+  for storage, (off, shape) in P.offsets.items():
+    (r,) = [r for r in tx.ranges if r[0] <= off < r[1]]
+    name = names_of.get(storage, [storage])[0]
+    assert (r[2] is None) == name.startswith("img/"), name
+    assert r[3] == (2.0 if name.startswith("txt/head/") else 1.0), name
+    want_wd = 1e-4 if name.endswith("/kernel") else 0.5e-4 if name == "txt/Embed_0/embedding" else 0.0
+    assert r[4] == pytest.approx(want_wd), name
+  for a, b in zip(tx.ranges, tx.ranges[1:]):
+    assert a[1] <= b[0] and (a[1] < b[0] or tuple(a[2:]) != tuple(b[2:]))   # disjoint, maximally merged
+    covered += a[1] - a[0]
+  assert covered + tx.ranges[-1][1] - tx.ranges[-1][0] == P.total
+  assert tx.n_state == sum(r[1] - r[0] for r in tx.ranges if r[2] is not None) < P.total
+  with pytest.raises(AssertionError):      # every parameter must be covered by a schedule pattern
+    bv_optax.make(dict(config, schedule=[("img/.*", None)]), P, sched_kw=dict(total_steps=10))
 
 
 def test_get_mixup_draws_a_at_least_one_half():
