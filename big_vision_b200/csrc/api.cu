@@ -189,6 +189,17 @@ int bv_scale_step(float* params, const float* grads, void* params_bf16, int64_t 
   return launch_scale_step(params, grads, params_bf16, n, lr_eff, wd_eff, grad_mult, clip_norm, gnorm_sq,
                            upd_sq, param_sq, S(stream));
 }
+int bv_adafactor_step(const bv_adafactor_args* a, void* stream) {
+  if (!a) { set_error("bv_adafactor_step: null args"); return BV_ERR_INVALID; }
+  AdafactorArgs g;
+  g.params = a->params; g.grads = a->grads; g.params_bf16 = a->params_bf16;
+  g.A = a->A; g.L = a->L; g.M = a->M; g.H = a->H; g.sA = a->sA; g.sL = a->sL; g.sM = a->sM;
+  g.mode = a->mode; g.vfull = a->vfull; g.red_h = a->red_h; g.red_l = a->red_l; g.nrm = a->nrm;
+  g.momentum = a->momentum; g.decay = a->decay; g.eps = a->eps; g.beta = a->beta; g.lr = a->lr_eff;
+  g.wd = a->wd_eff; g.grad_mult = a->grad_mult; g.clip_norm = a->clip_norm; g.gnorm_sq = a->gnorm_sq;
+  g.upd_sq = a->upd_sq; g.param_sq = a->param_sq;
+  return launch_adafactor(g, S(stream));
+}
 int bv_sumsq(const float* x, float* out, int64_t n, void* stream) {
   return launch_sumsq(x, out, n, S(stream));
 }

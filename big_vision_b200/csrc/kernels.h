@@ -123,6 +123,15 @@ struct AdamArgs {
 };
 int launch_adam(const AdamArgs& a, cudaStream_t s);
 int launch_sumsq(const float* x, float* out, int64_t n, cudaStream_t s);
+struct AdafactorArgs {
+  float* params; const float* grads; void* params_bf16;
+  int64_t A, L, M, H, sA, sL, sM;       // the tensor as a strided view [A, L, M, H] (H contiguous)
+  int mode;                              // 0 unfactored, 1 factored with d0 = H, 2 factored with d0 = L
+  float* vfull; float* red_h; float* red_l; float* nrm; void* momentum;
+  float decay, eps, beta, lr, wd, grad_mult, clip_norm;
+  const float* gnorm_sq; float* upd_sq; float* param_sq;
+};
+int launch_adafactor(const AdafactorArgs& a, cudaStream_t s);
 int launch_scale_step(float* params, const float* grads, void* params_bf16, int64_t n, float lr, float wd,
                       float grad_mult, float clip_norm, const float* gnorm_sq, float* upd_sq,
                       float* param_sq, cudaStream_t s);

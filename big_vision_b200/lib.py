@@ -49,6 +49,16 @@ class AdamArgs(ctypes.Structure):
               ("gnorm_sq", c_vp), ("step", c_i64), ("upd_sq", c_vp), ("param_sq", c_vp)]
 
 
+class AdafactorArgs(ctypes.Structure):
+  _fields_ = [("params", c_vp), ("grads", c_vp), ("params_bf16", c_vp),
+              ("A", c_i64), ("L", c_i64), ("M", c_i64), ("H", c_i64), ("sA", c_i64), ("sL", c_i64), ("sM", c_i64),
+              ("mode", c_i32),
+              ("vfull", c_vp), ("red_h", c_vp), ("red_l", c_vp), ("nrm", c_vp), ("momentum", c_vp),
+              ("decay", c_f32), ("eps", c_f32), ("beta", c_f32), ("lr_eff", c_f32), ("wd_eff", c_f32),
+              ("grad_mult", c_f32), ("clip_norm", c_f32),
+              ("gnorm_sq", c_vp), ("upd_sq", c_vp), ("param_sq", c_vp)]
+
+
 # name -> argtypes (restype is int unless noted).  Mirrors include/bv_b200.h one to one.
 SIGNATURES = {
     "bv_gemm": [ctypes.POINTER(GemmArgs), c_vp],
@@ -84,6 +94,7 @@ SIGNATURES = {
     "bv_softmax_xent": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
     "bv_adam_step": [ctypes.POINTER(AdamArgs), c_vp],
     "bv_sumsq": [c_vp, c_vp, c_i64, c_vp],
+    "bv_adafactor_step": [ctypes.POINTER(AdafactorArgs), c_vp],
     "bv_scale_step": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp],
     "bv_top1": [c_vp, c_i32, c_i64, c_i32, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp],
     "bv_retrieval_ranks": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp],
@@ -127,7 +138,7 @@ def check(rc, what):
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES = [0]
 _LAUNCHES_PER_CALL = {"bv_embed_bwd": 2, "bv_retrieval_ranks": 2, "bv_siglip_loss": 2,
-                      "bv_sigmoid_xent": 2, "bv_softmax_xent": 2}
+                      "bv_sigmoid_xent": 2, "bv_softmax_xent": 2, "bv_adafactor_step": 4}
 LOSS_WS_FLOATS = 8192      # BV_LOSS_WS_FLOATS
 
 

@@ -380,6 +380,23 @@ def scale_step(params, grads, params_bf16, *, lr_eff, wd_eff, grad_mult=1.0, cli
          clip_norm, _p(gnorm_sq), _p(upd_sq), _p(param_sq), _stream())
 
 
+def adafactor_step(P, tens, st, *, decay, eps, beta, lr_eff, wd_eff, grad_mult, clip_norm, gnorm_sq, upd_sq, param_sq):
+  """One BV-Adafactor update of the reference tensor `tens` (optax._AdafactorTensor) in place."""
+  A, Ld, M, H = tens.dims
+  sA, sL, sM = tens.strides
+  ptr = lambda buf: buf.data_ptr() + tens.offset * buf.element_size()
+  opt = lambda k: st[k].data_ptr() if k in st else None
+  args = L.AdafactorArgs(
+      params=ptr(P.flat), grads=ptr(P.grad), params_bf16=ptr(P.half), A=A, L=Ld, M=M, H=H, sA=sA, sL=sL, sM=sM,
+      mode=tens.mode, vfull=opt("vfull"), red_h=opt("red_h"), red_l=opt("red_l"), nrm=opt("nrm"),
+      momentum=opt("momentum"), decay=decay, eps=eps, beta=beta, lr_eff=lr_eff, wd_eff=wd_eff,
+      grad_mult=grad_mult, clip_norm=clip_norm, gnorm_sq=gnorm_sq.data_ptr(), upd_sq=upd_sq.data_ptr(),
+      param_sq=param_sq.data_ptr())
+  if not P.flat.is_cuda:
+    raise L.BvError("bv_adafactor_step needs CUDA tensors")
+  L.call("bv_adafactor_step", ctypes.byref(args), _stream())
+
+
 # ---- integer evaluation paths -------------------------------------------------------------------
 def top1(logits, labels=None, mask=None, want_idx=True):
   """argmax over classes (+ label gather and masked counts).  Returns (idx int32 [rows] or None,

@@ -15,8 +15,10 @@ launch -- two launches for the default config (decayed kernels | everything else
 get no launch and no optimizer state (optax_test.py:301-317) and do not count towards the clipping
 norm or `l2_grads` (optax_test.py:206-299, siglip.py:315-321).
 
-Not built: BV-Adafactor (`big_vision.scale_by_adafactor`, optax.py:187-214) and per-example clipping
-raise instead of silently doing something else.
+`big_vision.scale_by_adafactor` (optax.py:187-214) is the third inner transform: one `bv_adafactor_step`
+per reference tensor (factored second moments over the two largest axes when the second largest is
+>= min_dim_size_to_factor, bf16 momentum), see `_AdafactorTensor`.  Not built: clipping_threshold
+(clip_by_block_rms) and per-example clipping raise instead of silently doing something else.
 """
 import re
 
@@ -24,6 +26,48 @@ import torch
 
 from big_vision_b200 import ops
 from big_vision_b200 import utils as u
+
+
+class _AdafactorTensor:
+  """One reference tensor (a stored parameter or a named view of a fused one) as bv_adafactor_step sees
+  it: the strided view [A, L, M, H] of the flat buffers with {L, H} = optax's factored dims
+  (`_factored_dims`: the two largest axes, provided the second largest is >= min_dim_size_to_factor),
+  or a flat/2-D view for an unfactored tensor."""
+
+  def __init__(self, name, view, min_dim_size_to_factor):
+    import numpy as np
+    self.name, self.offset = name, view.storage_offset()
+    shape, stride = list(view.shape), list(view.stride())
+    self.numel = int(np.prod(shape))
+    order = np.argsort(shape, kind="stable")
+    if len(shape) < 2 or shape[order[-2]] < min_dim_size_to_factor:
+      self.mode = 0
+      if view.is_contiguous():
+        self.dims, self.strides = (1, 1, 1, self.numel), (0, 0, 0)
+      elif len(shape) == 2 and stride[1] == 1:
+        self.dims, self.strides = (1, shape[0], 1, shape[1]), (0, stride[0], 0)
+      else:
+        raise NotImplementedError(f"adafactor: unfactored strided tensor {name} {shape} {stride}")
+      return
+    d1, d0 = int(order[-2]), int(order[-1])          # optax: (second largest, largest)
+    lo, hi = min(d0, d1), max(d0, d1)
+    if hi != len(shape) - 1 or stride[hi] != 1:
+      raise NotImplementedError(f"adafactor: factored axes of {name} {shape} are not (.., L, .., H)")
+
+    def merged(axes):                                # (size, stride) of a run of axes read as one
+      size = int(np.prod([shape[i] for i in axes])) if axes else 1
+      for i, j in zip(axes, axes[1:]):
+        if stride[i] != stride[j] * shape[j]:
+          raise NotImplementedError(f"adafactor: axes {axes} of {name} do not merge")
+      return size, (stride[axes[-1]] if axes else 0)
+
+    (A, sA), (M, sM) = merged(list(range(lo))), merged(list(range(lo + 1, hi)))
+    self.dims, self.strides = (A, shape[lo], M, shape[hi]), (sA, stride[lo], sM)
+    self.mode = 1 if d0 == hi else 2
+
+  def state_sizes(self):
+    A, L, M, H = self.dims
+    return {"vfull": self.numel} if self.mode == 0 else {"red_h": A * L * M, "red_l": A * M * H, "nrm": A * M}
 
 
 def _first_match(patterns, names):
@@ -55,8 +99,17 @@ class Chain:
       self.step_size = None
     elif name == "scale":
       self.step_size = float(kw.pop("step_size"))
+    elif name == "big_vision.scale_by_adafactor":
+      self.af = dict(min_dim_size_to_factor=kw.pop("min_dim_size_to_factor", 32), decay_rate=kw.pop("decay_rate", 0.8),
+                     decay_offset=kw.pop("decay_offset", 0), beta2_cap=kw.pop("beta2_cap", 0.999),
+                     momentum=kw.pop("momentum", 0.9), eps=kw.pop("eps", 1e-30))
+      if kw.pop("clipping_threshold", None):
+        raise NotImplementedError("adafactor clipping_threshold (optax.clip_by_block_rms)")
+      if kw.pop("dtype_momentum", "bfloat16") not in ("bfloat16", torch.bfloat16):
+        raise NotImplementedError("adafactor momentum accumulator other than bfloat16")
+      self.step_size = None
     else:
-      raise NotImplementedError(f"optax_name={name}: built are scale_by_adam and scale")
+      raise NotImplementedError(f"optax_name={name}: built are scale_by_adam, scale, big_vision.scale_by_adafactor")
     if kw:
       raise NotImplementedError(f"{name} options {sorted(kw)}")
     if config.get("grad_clip_per_example"):
@@ -95,6 +148,7 @@ class Chain:
     for a in P.aliases.values():
       names_of.setdefault(a.storage, []).append(a.name)
     uncovered, self.ranges = [], []      # ranges: [lo, hi, sched slot | None, lr mult, wd]
+    self.per_storage = []                # (storage, sched slot | None, lr mult, wd)
     for storage, (off, shape) in sorted(P.offsets.items(), key=lambda kv: kv[1][0]):
       names = names_of.get(storage, [storage])
       si = _first_match(sched_pat, names)
@@ -105,6 +159,7 @@ class Chain:
       wi = _first_match(wd_pat, names) if wd_pat else None
       key = (sched_slot[si], 1.0 if li is None else float(lr_mults[li][1]),
              0.0 if wi is None else wd * float(wd_mults[wi][1]))
+      self.per_storage.append((storage, *key))
       n = 1
       for dim in shape:
         n *= dim
@@ -122,6 +177,19 @@ class Chain:
       if slot is not None:
         n_state += hi - lo
     self.n_state = n_state
+    # adafactor works tensor by tensor on the REFERENCE tensors (the named views of fused storage)
+    self.tensors = []
+    if self.inner == "big_vision.scale_by_adafactor":
+      views_of = {}
+      for a in P.aliases.values():
+        views_of.setdefault(a.storage, []).append(a)
+      for storage, slot, lr_mult, wd in self.per_storage:
+        if slot is None:
+          continue
+        base = P.f(storage)
+        for nm, view in ([(a.name, a.view(base)) for a in views_of[storage]] if storage in views_of
+                         else [(storage, base)]):
+          self.tensors.append((_AdafactorTensor(nm, view, self.af["min_dim_size_to_factor"]), slot, lr_mult, wd))
 
   def init(self, P):
     dev = P.flat.device
@@ -129,6 +197,13 @@ class Chain:
     if self.inner == "scale_by_adam":
       state["mu"] = torch.zeros(self.n_state, dtype=self.mu_dtype, device=dev)
       state["nu"] = torch.zeros(self.n_state, dtype=torch.float32, device=dev)
+    if self.inner == "big_vision.scale_by_adafactor":
+      state["af"] = []
+      for t, *_ in self.tensors:
+        st = {k: torch.zeros(n, dtype=torch.float32, device=dev) for k, n in t.state_sizes().items()}
+        if self.af["momentum"]:
+          st["momentum"] = torch.zeros(t.numel, dtype=torch.bfloat16, device=dev)
+        state["af"].append(st)
     return state
 
   def update(self, P, opt, grad_mult=1.0):
@@ -140,6 +215,16 @@ class Chain:
       ops.sumsq(P.grad[lo:hi], sc[0:1])
     scheds = [fn(opt["count"]) for fn in self.sched_fns]   # evaluated at the pre-increment count
     step = opt["count"] + 1
+    if self.inner == "big_vision.scale_by_adafactor":
+      # second-moment decay of this step (optax.py:196-199): min(beta2_cap, 1 - (t + 1)^-decay_rate), float32
+      import numpy as np
+      t = np.float32(opt["count"] - self.af["decay_offset"]) + np.float32(1.0)
+      decay = float(min(np.float32(self.af["beta2_cap"]), np.float32(1.0) - t ** np.float32(-self.af["decay_rate"])))
+      for (tens, slot, lr_mult, wd), st in zip(self.tensors, opt["af"]):
+        ops.adafactor_step(P, tens, st, decay=decay, eps=self.af["eps"], beta=self.af["momentum"] or 0.0,
+                           lr_eff=scheds[slot] * self.lr * lr_mult, wd_eff=scheds[slot] * wd, grad_mult=grad_mult,
+                           clip_norm=self.clip, gnorm_sq=sc[0:1], upd_sq=sc[1:2], param_sq=sc[2:3])
+      trained = []
     for (lo, hi, slot, lr_mult, wd), so in trained:
       sched = scheds[slot]
       common = dict(wd_eff=sched * wd, grad_mult=grad_mult, clip_norm=self.clip, gnorm_sq=sc[0:1],

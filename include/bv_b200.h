@@ -239,6 +239,27 @@ int bv_scale_step(float* params, const float* grads, void* params_bf16, int64_t 
                   float wd_eff, float grad_mult, float clip_norm, const float* gnorm_sq, float* upd_sq,
                   float* param_sq, void* stream);
 
+/* BV-Adafactor (`big_vision.scale_by_adafactor`, optax.py:187-214: optax.scale_by_factored_rms with
+ * decay min(beta2_cap, 1 - (t+1)^-0.8), min_dim_size_to_factor 32, eps 1e-30, then optax.ema(momentum,
+ * debias=False, bf16 accumulator)) for ONE reference tensor given as the strided view [A, L, M, H] of the
+ * flat buffers (element strides sA, sL, sM; H contiguous), inside the same outer chain as bv_adam_step:
+ *   mode 0  unfactored: vfull [A*L*M*H] <- decay*vfull + (1-decay)(g'^2+eps);  u = g' * vfull^-1/2
+ *   mode 1  factored, largest axis d0 = H, d1 = L;   mode 2  factored, d0 = L, d1 = H:
+ *           red_h [A,L,M] <- ema(mean_H(g'^2+eps)), red_l [A,M,H] <- ema(mean_L(g'^2+eps)),
+ *           nrm [A,M] = mean_{d1}(R0) (scratch), u = g' * (R0/nrm)^-1/2 * R1^-1/2   (R0 = stat reduced over d0)
+ *   momentum (bf16 [A*L*M*H], may be NULL): m <- beta*m + (1-beta)*u, u = m (pre-rounding value)
+ *   p += -(lr_eff * u + wd_eff * p);  g' = g * grad_mult * clip(gnorm) as in bv_adam_step.
+ * `decay` is the step's second-moment decay, computed by the caller. */
+typedef struct bv_adafactor_args {
+  float* params; const float* grads; void* params_bf16;
+  int64_t A, L, M, H, sA, sL, sM;
+  int32_t mode;
+  float* vfull; float* red_h; float* red_l; float* nrm; void* momentum;
+  float decay, eps, beta, lr_eff, wd_eff, grad_mult, clip_norm;
+  const float* gnorm_sq; float* upd_sq; float* param_sq;
+} bv_adafactor_args;
+int bv_adafactor_step(const bv_adafactor_args* args, void* stream);
+
 /* ---------------------------------------------------------------------------------
  * Integer evaluation paths (bit-exact index arithmetic)
  * bv_top1 -- evaluators/classification.py:46-52 and the zero-shot argmax of

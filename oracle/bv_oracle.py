@@ -320,6 +320,43 @@ def adam_reference(p, g, m, v, step, *, lr, b1, b2, eps, wd, sched=1.0, clip=0.0
   return p + upd, m, v
 
 
+def adafactor_reference(p, g, state, count, *, lr, wd=0.0, sched=1.0, min_dim_size_to_factor=32,
+                        decay_rate=0.8, decay_offset=0, beta2_cap=0.999, momentum=0.9, eps=1e-30):
+  """`big_vision.scale_by_adafactor` (optax.py:187-214) inside the chain of optax.py:143-149 for ONE
+  tensor, numpy float64 (momentum accumulator rounded to bf16 like `dtype_momentum`).  The factored
+  second moment is optax's `scale_by_factored_rms` (optax is an un-vendored, un-pinned dependency of
+  the reference, requirements.txt:8; restated from its published algorithm, `_factored_dims` /
+  `_update` of optax/_src/factorized.py):
+    d1, d0 = the second-largest and largest axes (np.argsort), factored iff shape[d1] >= min_dim_size
+    v_row = ema(mean_{d0}(g^2 + eps)), v_col = ema(mean_{d1}(g^2 + eps)), decay_t = min(cap, 1 - (t+1)^-0.8)
+    u = g * (v_row / mean_{d1}(v_row))^-1/2 [expanded at d0] * v_col^-1/2 [expanded at d1]
+  `state` is a dict (empty on the first call); returns (new_p, new_state)."""
+  g = np.asarray(g, np.float64)
+  t = np.float32(count - decay_offset) + np.float32(1.0)
+  decay = float(min(np.float32(beta2_cap), np.float32(1.0) - t ** np.float32(-decay_rate)))
+  shape = g.shape
+  order = np.argsort(shape, kind="stable") if len(shape) else []
+  st = dict(state)
+  if len(shape) >= 2 and shape[order[-2]] >= min_dim_size_to_factor:
+    d1, d0 = int(order[-2]), int(order[-1])
+    gsq = g * g + eps
+    v_row = decay * st.get("v_row", 0.0) + (1 - decay) * gsq.mean(axis=d0)
+    v_col = decay * st.get("v_col", 0.0) + (1 - decay) * gsq.mean(axis=d1)
+    reduced_d1 = d1 - 1 if d1 > d0 else d1
+    row_col_mean = v_row.mean(axis=reduced_d1, keepdims=True)
+    u = g * np.expand_dims((v_row / row_col_mean) ** -0.5, d0) * np.expand_dims(v_col ** -0.5, d1)
+    st.update(v_row=v_row, v_col=v_col)
+  else:
+    v = decay * st.get("v", 0.0) + (1 - decay) * (g * g + eps)
+    u = g * v ** -0.5
+    st["v"] = v
+  if momentum:
+    m = momentum * st.get("m", 0.0) + (1 - momentum) * u          # optax.ema, debias=False
+    st["m"] = torch.tensor(m).to(torch.float32).to(torch.bfloat16).double().numpy()   # bf16 accumulator
+    u = m
+  return p - sched * (lr * u + wd * p), st
+
+
 # ----------------------------------------------------------------------------------------------
 # Integer evaluation paths (numpy; test infrastructure like the rest of this file)
 # ----------------------------------------------------------------------------------------------

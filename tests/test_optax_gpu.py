@@ -120,4 +120,66 @@ def test_frozen_no_state_and_uncovered_params():
     bv_optax.make(dict(lr=0.01, schedule=[("small", dict(decay_type="cosine"))]), P,
                   sched_kw=dict(total_steps=1))
   with pytest.raises(NotImplementedError):
-    bv_optax.make(dict(lr=0.01, optax_name="big_vision.scale_by_adafactor"), P, sched_kw=dict(total_steps=1))
+    bv_optax.make(dict(lr=0.01, optax_name="lion"), P, sched_kw=dict(total_steps=1))
+
+
+def test_adafactor_state_size_known_answer():
+  """optax_test.py:320-341: a [1024, 1024] kernel keeps 2 * 1024 second-moment statistics (+ scalars)."""
+  from big_vision_b200 import optax as bv_optax
+  P = _params({"Dense_0/kernel": np.zeros((1024, 1024), np.float32)})
+  tx, _ = bv_optax.make(dict(optax_name="big_vision.scale_by_adafactor", lr=0.01, schedule=dict(decay_type="linear")),
+                        P, sched_kw=dict(global_batch_size=1, total_steps=1))
+  state = tx.init(P)
+  (st,) = state["af"]
+  assert st["red_h"].numel() + st["red_l"].numel() == 2 * 1024 and "vfull" not in st
+
+
+@pytest.mark.parametrize("momentum", [0.9, 0.0])
+def test_adafactor_matches_oracle(momentum):
+  """BV-Adafactor on every tensor geometry of the path -- Dense [in,out] with either axis largest,
+  DenseGeneral q/k/v [d,h,dh] and out [h,dh,d] as views of fused storage, scan-stacked kernels,
+  unfactored small / 1-D tensors -- against the numpy restatement of optax's factored rms, 4 steps,
+  with weight decay, gradient clipping and a schedule in the chain."""
+  from big_vision_b200 import engine as E, optax as bv_optax
+  from oracle import bv_oracle as O
+  rng = np.random.default_rng(0)
+  d, h, dh = 96, 3, 32
+  rnd = lambda rng_, shape: rng_.standard_normal(shape).astype(np.float32)
+  specs = [E.ParamSpec("a/kernel", (64, 96), rnd), E.ParamSpec("b/kernel", (96, 64), rnd),
+           E.ParamSpec("att/qkv/kernel", (d, 3 * d), rnd), E.ParamSpec("att/out_proj/kernel", (d, d), rnd),
+           E.ParamSpec("stk/kernel", (2, 48, 40), rnd), E.ParamSpec("small/kernel", (16, 20), rnd),
+           E.ParamSpec("a/bias", (100,), rnd), E.ParamSpec("pos_embedding", (1, 50, 64), rnd)]
+  aliases = [E.Alias(f"att/{nm}/kernel", "att/qkv/kernel", lambda t, i=i: t[:, i * d:(i + 1) * d].unflatten(1, (h, dh)))
+             for i, nm in enumerate(["query", "key", "value"])]
+  aliases.append(E.Alias("att/out/kernel", "att/out_proj/kernel", lambda t: t.unflatten(0, (h, dh))))
+  P = E.FlatParams(specs, aliases, "cuda").init(1)
+  config = dict(optax_name="big_vision.scale_by_adafactor", optax=dict(momentum=momentum), lr=0.05, wd=0.01,
+                grad_clip_norm=1.0, schedule=dict(decay_type="cosine", warmup_steps=1))
+  tx, (sched_fn,) = bv_optax.make(config, P, sched_kw=dict(total_steps=10))
+  state = tx.init(P)
+  modes = {t.name: t.mode for t, *_ in tx.tensors}
+  assert modes["a/kernel"] == 1 and modes["b/kernel"] == 2 and modes["att/query/kernel"] == 2
+  assert modes["att/out/kernel"] == 1 and modes["small/kernel"] == 0 and modes["a/bias"] == 0
+  ref_p = {k: v.astype(np.float64) for k, v in P.numpy_tree("f").items()}
+  ref_state = {k: {} for k in ref_p}
+  for step in range(4):
+    P.zero_grad()
+    grads = {}
+    for k, v in P.tree("g").items():
+      gk = rng.standard_normal(tuple(v.shape)).astype(np.float32) * (0.1 + step)
+      v.copy_(torch.from_numpy(gk))
+      grads[k] = gk.astype(np.float64)
+    gnorm = np.sqrt(sum((g * g).sum() for g in grads.values()))
+    factor = 1.0 if gnorm < 1.0 else 1.0 / gnorm
+    tx.update(P, state)
+    sched = sched_fn(step)
+    for k in ref_p:
+      wd = 0.01 if k.endswith("/kernel") else 0.0
+      ref_p[k], ref_state[k] = O.adafactor_reference(ref_p[k], grads[k] * factor, ref_state[k], step, lr=0.05,
+                                                     wd=wd, sched=sched, momentum=momentum)
+    got = P.numpy_tree("f")
+    for k in ref_p:
+      np.testing.assert_allclose(got[k], ref_p[k], rtol=3e-3 if momentum else 2e-5, atol=1e-5,
+                                 err_msg=f"{k} step {step}")
+  # the bf16 shadow follows the master copy
+  np.testing.assert_allclose(P.numpy_tree("h")["a/kernel"], got["a/kernel"], rtol=1e-2, atol=1e-3)

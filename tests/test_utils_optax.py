@@ -58,8 +58,18 @@ def _tiny_params():
 def test_make_rejects_unbuilt_configurations():
   P = _tiny_params()
   with pytest.raises(NotImplementedError):
-    bv_optax.make(dict(optax_name="big_vision.scale_by_adafactor", schedule={}), P,
-                  sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
+    bv_optax.make(dict(optax_name="big_vision.scale_by_adafactor", optax=dict(clipping_threshold=1.0),
+                       schedule={}), P, sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
+  with pytest.raises(NotImplementedError):
+    bv_optax.make(dict(optax_name="lion", schedule={}), P, sched_kw=dict(total_steps=10))
+  # BV-Adafactor on the two-tower tree: q/k/v kernels are factored per head over (d, dh), Dense
+  # kernels over (in, out); biases, LayerNorm parameters and the 16x16x3xd patch kernel are not
+  tx, _ = bv_optax.make(dict(optax_name="big_vision.scale_by_adafactor", schedule={}), P,
+                        sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
+  modes = {t.name: (t.mode, t.dims) for t, *_ in tx.tensors}
+  assert modes["img/Transformer/encoderblock_0/MultiHeadDotProductAttention_0/query/kernel"] == (1, (1, 64, 1, 64))   # d == dh tie: argsort order
+  assert modes["img/Transformer/encoderblock_0/MlpBlock_0/Dense_0/kernel"] == (1, (1, 64, 1, 128))
+  assert modes["img/embedding/kernel"][0] == 0 and modes["img/Transformer/encoderblock_0/LayerNorm_0/scale"][0] == 0
   tx, fns = bv_optax.make(dict(optax_name="scale_by_adam", optax=dict(b2=0.95), lr=1e-3, wd=1e-4,
                                grad_clip_norm=1.0, schedule=dict(decay_type="cosine", warmup_steps=2)),
                           P, sched_kw=dict(total_steps=10, batch_size=8, data_size=100))
