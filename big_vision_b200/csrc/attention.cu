@@ -36,6 +36,7 @@ struct FwdDev {
   float scale_log2;   // scale * log2(e)
   float* lse;         // [B, H, Nq]
   long long* dbg;     // optional timeline of CTA 0 (bring-up aid, BV_ATTN_DBG=1), else null
+  int sm_var;         // softmax tuning variant (BV_ATTN_SM, bit 0 = independent max / sum chains)
 };
 
 // dbg[(tile_i * 16 + event)] = clock64() for the first 32 tiles of CTA 0
@@ -82,8 +83,12 @@ struct SoftmaxCtx {
   } while (0)
 
 // NU = number of 8-column units per thread (compile time; 0 = run time, up to 16)
-template <int NU>
+// ALL_MUFU: every exponential on MUFU.EX2 (BV_ATTN_SM >> 2 == 2, the default) instead of alternating
+// 8-column units with the FMA-pipe polynomial.  (Independent max / sum chains were tried on the
+// streaming kernel and measured no different; the ILP switch is kept off.)
+template <int NU, bool ALL_MUFU>
 __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
+  constexpr bool ILP = false;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3, hf = warp >> 2;
   const int row = quarter * 32 + lane;
@@ -118,7 +123,7 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
     if (lane == 0) mbar_arrive(c.s_empty0 + 8u * bf);
 
     // row maximum of the raw scores (scale > 0, so max commutes with the scaling)
-    float mx = -INFINITY;
+    float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       if (UNIT_ON(u)) {
@@ -127,23 +132,26 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
           float sc = __uint_as_float(sv[u][j]);
           if (u * 8 + j >= valid) sc = -INFINITY;     // padded key columns
           sv[u][j] = __float_as_uint(sc);
-          mx = fmaxf(mx, sc);
+          float& m = mxa[ILP ? (j & 3) : 0];
+          m = fmaxf(m, sc);
         }
       }
     }
+    float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
     xch[hf * 128 + row] = mx;
     SM_DBG(13, i);
     named_bar_sync(2, 256);
     mx = fmaxf(mx, xch[(hf ^ 1) * 128 + row]);
     SM_DBG(4, i);
     const float mxs = mx * scale_log2;
-    float sum = 0.f;
+    float sma[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       if (UNIT_ON(u)) {
         float e[8];
-        // exp2(scale * s - scale * max); units alternate between MUFU and the FMA-pipe polynomial
-        if (u & 1) {
+        // exp2(scale * s - scale * max); ALL_MUFU (default since round 2: measured faster, the FMA
+        // pipe is the co-bottleneck) or units alternating between MUFU and the FMA-pipe polynomial
+        if (!ALL_MUFU && (u & 1)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) e[j] = ex2_poly(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
         } else {
@@ -151,7 +159,7 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
           for (int j = 0; j < 8; ++j) e[j] = ex2_mufu(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += e[j];
+        for (int j = 0; j < 8; ++j) sma[ILP ? (j & 3) : 0] += e[j];
         // packed in place: sv[u][0..3] now hold the 8 bf16 probabilities of this unit
         sv[u][0] = pack_bf16(e[0], e[1]); sv[u][1] = pack_bf16(e[2], e[3]);
         sv[u][2] = pack_bf16(e[4], e[5]); sv[u][3] = pack_bf16(e[6], e[7]);
@@ -170,6 +178,7 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
                      "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
       }
     }
+    float sum = (sma[0] + sma[1]) + (sma[2] + sma[3]);
     xch[256 + hf * 128 + row] = sum;
     SM_DBG(15, i);
     fence_proxy_async();
@@ -377,10 +386,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     c.NKP = p.NKP; c.Nk = p.Nk; c.Nq = p.Nq; c.QT = p.QT; c.nbuf = p.nbuf; c.scale_log2 = p.scale_log2;
     c.lse = p.lse; c.dbg = p.dbg;
     const int nunits = p.NKP >> 4;
-    if (nunits == 13) softmax_warpgroups<13>(c);
-    else if (nunits == 4) softmax_warpgroups<4>(c);
-    else if (nunits == 16) softmax_warpgroups<16>(c);
-    else softmax_warpgroups<0>(c);
+    if (p.sm_var >> 2 == 2) {
+      if (nunits == 13) softmax_warpgroups<13, true>(c);
+      else if (nunits == 4) softmax_warpgroups<4, true>(c);
+      else if (nunits == 16) softmax_warpgroups<16, true>(c);
+      else softmax_warpgroups<0, true>(c);
+    } else {
+      if (nunits == 13) softmax_warpgroups<13, false>(c);
+      else if (nunits == 4) softmax_warpgroups<4, false>(c);
+      else if (nunits == 16) softmax_warpgroups<16, false>(c);
+      else softmax_warpgroups<0, false>(c);
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -838,6 +854,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bf16* __restrict__ p_do = pin_reg(p.d_o);
     const long long p_ldo = p.ldo, p_bso = p.bso, p_lddo = p.lddo, p_bsdo = p.bsdo;
     const int wmode = pin_reg(p.variant) & 3;
+    const bool mixed_exp = (pin_reg(p.variant) & 4) != 0;
     // ---- prologue of item `pit`: delta = rowsum(O o dO) and lse (log2 units) for its 256 row slots,
     // straight from global memory while the TMA loads are in flight; buffers alternate per item
     auto prologue = [&](int pit) {
@@ -911,15 +928,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + hf * 64, t0);
             tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + hf * 64 + 32, t1);
             tmem_ld_wait();
+            // No masking is needed here: padded query rows have lse = +inf (so P ~ 0), zero dO and
+            // zero Q rows; padded key columns only feed dV/dK rows that the TMA store clips and a
+            // dQ product against zero-filled K rows.  Everything stays finite.
+            // Exponentials: all on MUFU (BV_BWD_VARIANT bit 2 clear, the default since round 2) or
+            // alternating between MUFU and the FMA-pipe polynomial (see ex2_poly).
+            if (!mixed_exp) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              // No masking is needed here: padded query rows have lse = +inf (so P ~ 0), zero dO and
-              // zero Q rows; padded key columns only feed dV/dK rows that the TMA store clips and a
-              // dQ product against zero-filled K rows.  Everything stays finite.
-              // Exponentials alternate between MUFU and the FMA-pipe polynomial (see ex2_poly).
-              const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
-              const float xa = fmaf(sj, p_scale_log2, -l2);
-              pe[j] = (j & 2) ? ex2_poly(xa) : ex2_mufu(xa);
+              for (int j = 0; j < 64; ++j) {
+                const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
+                pe[j] = ex2_mufu(fmaf(sj, p_scale_log2, -l2));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
+                const float xa = fmaf(sj, p_scale_log2, -l2);
+                pe[j] = (j & 2) ? ex2_poly(xa) : ex2_mufu(xa);
+              }
             }
           }
           if (tid == 0) BWD_DBG(1, pair_cnt);
@@ -1023,6 +1049,7 @@ int launch_attention_fwd(const AttnArgs& a, cudaStream_t s) {
   if (use_stream_fwd(a)) return launch_attention_fwd_stream(a, s);
   FwdDev p;
   p.dbg = attn_debug_buffer();
+  { const char* e = getenv("BV_ATTN_SM"); p.sm_var = e ? atoi(e) : 8; }   // bits 2..: 2 = all exponentials on MUFU
   p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
   p.QT = (a.Nq + TQ - 1) / TQ;
   p.NKP = (a.Nk + 15) / 16 * 16;

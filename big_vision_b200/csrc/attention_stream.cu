@@ -38,6 +38,7 @@ constexpr int F2_O_OFF = F2_P_OFF + 2 * 2 * TILE_BYTES;       // 16 KB staging o
 constexpr int F2_ST_OFF = F2_O_OFF + TILE_BYTES;              // stats [w][buf][m|l][128] fp32 = 4 KB
 constexpr int F2_BAR_OFF = F2_ST_OFF + 2 * 2 * 2 * 128 * 4;
 constexpr int F2_SMEM = F2_BAR_OFF + 512 + 1024;
+constexpr int F2_DEFAULT_VAR = 9;               // softmax variant (see softmax_block); BV_ATTN_SM overrides
 
 struct Fwd2Dev {
   int tiles;          // B * H * QT
@@ -46,12 +47,24 @@ struct Fwd2Dev {
   float* lse;         // [B, H, Nq] or null
 };
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // three-input max (sm_100)
+  return d;
+}
+
 // One block of scores for one softmax warpgroup thread: load, (mask), max, exponentials, pack.
 // FULL: all 128 columns are real keys (no masking, compile-time trip counts).
-template <bool FULL>
+// VAR (tuning switch, BV_ATTN_SM): bit 0 = four independent max / sum chains instead of one serial
+// chain of 128 (each warp scheduler holds only two softmax warps, so a 128-deep dependent chain is
+// pure latency); bit 1 = three-input max; bits 2.. = exponential split: 0 alternate 8-column units
+// between MUFU and the FMA-pipe polynomial, 1 = one unit in four on the polynomial, 2 = all MUFU.
+template <bool FULL, int VAR>
 __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, uint32_t sw, int valid,
                                               float scale_log2, uint32_t s_empty_bar, uint32_t p_empty_bar,
                                               uint32_t p_empty_parity, float& mxs_out, float& sum_out) {
+  constexpr bool ILP4 = (VAR & 1) != 0, MAX3 = (VAR & 2) != 0;
+  constexpr int SPLIT = VAR >> 2;
   const int lane = threadIdx.x & 31;
   // units of 8 columns that take part in the P.V product: whole 16-key MMA steps
   const int nunits = FULL ? 16 : ((valid + 15) >> 4) * 2;
@@ -66,53 +79,63 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, u
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(s_empty_bar);
-  float mx = -INFINITY, sum = 0.f, mxs = 0.f;
-  {
+  float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float sma[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      if (UNIT_ON(u)) {
+  for (int u = 0; u < 16; ++u) {
+    if (UNIT_ON(u)) {
+      if (!FULL) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float sc = __uint_as_float(sv[u][j]);
-          if (!FULL) {
-            if (u * 8 + j >= valid) sc = -INFINITY;     // key columns past Nk (zero-filled K rows)
-            sv[u][j] = __float_as_uint(sc);
-          }
-          mx = fmaxf(mx, sc);
-        }
+        for (int j = 0; j < 8; ++j)
+          if (u * 8 + j >= valid) sv[u][j] = 0xff800000u;     // -inf: key columns past Nk
       }
-    }
-    mxs = mx * scale_log2;
+      float& m = mxa[ILP4 ? (u & 3) : 0];
+      if (MAX3) {
+        m = max3(m, __uint_as_float(sv[u][0]), __uint_as_float(sv[u][1]));
+        const float a = max3(__uint_as_float(sv[u][2]), __uint_as_float(sv[u][3]), __uint_as_float(sv[u][4]));
+        const float b = max3(__uint_as_float(sv[u][5]), __uint_as_float(sv[u][6]), __uint_as_float(sv[u][7]));
+        m = max3(m, a, b);
+      } else {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      if (UNIT_ON(u)) {
-        float e[8];
-        // exp2(scale * s - scale * max); units alternate between MUFU and the FMA-pipe polynomial
-        if (u & 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = ex2_poly(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = ex2_mufu(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += e[j];
-        sv[u][0] = pack_bf16(e[0], e[1]); sv[u][1] = pack_bf16(e[2], e[3]);
-        sv[u][2] = pack_bf16(e[4], e[5]); sv[u][3] = pack_bf16(e[6], e[7]);
+        for (int j = 0; j < 8; ++j) m = fmaxf(m, __uint_as_float(sv[u][j]));
       }
     }
   }
+  const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+  const float mxs = mx * scale_log2;
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    if (UNIT_ON(u)) {
+      float e[8];
+      // exp2(scale * s - scale * max), split between MUFU and the FMA-pipe polynomial
+      const bool poly = SPLIT == 0 ? (u & 1) : SPLIT == 1 ? ((u & 3) == 3) : false;
+      if (poly) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = ex2_poly(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = ex2_mufu(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
+      }
+      if (ILP4) {
+        sma[0] += e[0] + e[4]; sma[1] += e[1] + e[5]; sma[2] += e[2] + e[6]; sma[3] += e[3] + e[7];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sma[0] += e[j];
+      }
+      sv[u][0] = pack_bf16(e[0], e[1]); sv[u][1] = pack_bf16(e[2], e[3]);
+      sv[u][2] = pack_bf16(e[4], e[5]); sv[u][3] = pack_bf16(e[6], e[7]);
+    }
+  }
+  const float sum = (sma[0] + sma[1]) + (sma[2] + sma[3]);
   // the P buffer is free once the P.V product of this warpgroup's previous block has retired
   mbar_wait(p_empty_bar, p_empty_parity);
-  {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      if (UNIT_ON(u)) {
-        const uint32_t k = static_cast<uint32_t>(u);
-        const uint32_t addr = p_row + (k >> 3) * TILE_BYTES + (((k & 7u) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sv[u][0]),
-                     "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
-      }
+  for (int u = 0; u < 16; ++u) {
+    if (UNIT_ON(u)) {
+      const uint32_t k = static_cast<uint32_t>(u);
+      const uint32_t addr = p_row + (k >> 3) * TILE_BYTES + (((k & 7u) ^ sw) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sv[u][0]),
+                   "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
     }
   }
 #undef UNIT_ON
@@ -120,6 +143,7 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, u
   sum_out = sum;
 }
 
+template <int VAR>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -364,9 +388,9 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         float mxs, sum;
         if (valid >= BK)
-          softmax_block<true>(s_addr, p_row, sw, BK, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
+          softmax_block<true, VAR>(s_addr, p_row, sw, BK, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
         else
-          softmax_block<false>(s_addr, p_row, sw, valid, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
+          softmax_block<false, VAR>(s_addr, p_row, sw, valid, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
         // statistics of this block for the epilogue; the slot is free once the epilogue has consumed
         // the previous block that used this (w, ob) buffer pair
         mbar_wait(o_empty(w, ob), ((n >> 1) & 1u) ^ 1u);
@@ -421,6 +445,7 @@ struct Bwd2Dev {
   const float* lse;    // [B, H, Nq]
   const float* delta;  // [B, H, Nq]
   float* dk_colsum; float* dv_colsum;   // optional [H*64] bias gradients
+  int variant;         // BV_BWD_VARIANT: bit 2 = alternate MUFU / polynomial exponentials (default: all MUFU)
 };
 
 __global__ void __launch_bounds__(B2_THREADS, 1)
@@ -678,6 +703,7 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float p_scale = pin_reg(p.scale), p_scale_log2 = pin_reg(p.scale_log2);
     const float* __restrict__ p_lse = pin_reg(p.lse);
     const float* __restrict__ p_delta = pin_reg(p.delta);
+    const bool mixed_exp = (pin_reg(p.variant) & 4) != 0;
     uint32_t pc = 0;
     for (int gi = 0; gi < my_groups; ++gi) {
       const int group = blockIdx.x + gi * gridDim.x;
@@ -699,13 +725,21 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + hf * 64, t0);
           tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL + hf * 64 + 32, t1);
           tmem_ld_wait();
+          // no key masking needed: padded key columns only feed dV/dK rows that the TMA store clips
+          // and a dQ product against zero-filled K rows; everything stays finite
+          if (!mixed_exp) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            // no key masking needed: padded key columns only feed dV/dK rows that the TMA store clips
-            // and a dQ product against zero-filled K rows; everything stays finite
-            const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
-            const float xa = fmaf(sj, p_scale_log2, -l2);
-            pe[j] = (j & 2) ? ex2_poly(xa) : ex2_mufu(xa);
+            for (int j = 0; j < 64; ++j) {
+              const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
+              pe[j] = ex2_mufu(fmaf(sj, p_scale_log2, -l2));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
+              const float xa = fmaf(sj, p_scale_log2, -l2);
+              pe[j] = (j & 2) ? ex2_poly(xa) : ex2_mufu(xa);
+            }
           }
         }
         mbar_wait(pds_empty, pp ^ 1u);
@@ -824,12 +858,22 @@ int launch_attention_fwd_stream(const AttnArgs& a, cudaStream_t s) {
   if ((rc = make_tmap_bnd(&tmK, a.k, cols, a.Nk, a.B, a.ldk, a.bsk, BK))) return rc;
   if ((rc = make_tmap_bnd(&tmV, a.v, cols, a.Nk, a.B, a.ldv, a.bsv, BK))) return rc;
   if ((rc = make_tmap_bnd(&tmO, a.o, cols, a.Nq, a.B, a.ldo, a.bso, TQ))) return rc;
-  rc = check_cuda(cudaFuncSetAttribute(attn_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       F2_SMEM), "cudaFuncSetAttribute(attn_fwd_stream)");
-  if (rc) return rc;
   const int sms = num_sms();
   const int grid = p.tiles < sms ? p.tiles : sms;
-  attn_fwd_stream_kernel<<<grid, F2_THREADS, F2_SMEM, s>>>(tmQ, tmK, tmV, tmO, p);
+  int var = F2_DEFAULT_VAR;
+  { const char* e = getenv("BV_ATTN_SM"); if (e) var = atoi(e); }
+#define F2_LAUNCH(V)                                                                                           \
+  case V:                                                                                                      \
+    rc = check_cuda(cudaFuncSetAttribute(attn_fwd_stream_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         F2_SMEM), "cudaFuncSetAttribute(attn_fwd_stream)");                    \
+    if (rc) return rc;                                                                                         \
+    attn_fwd_stream_kernel<V><<<grid, F2_THREADS, F2_SMEM, s>>>(tmQ, tmK, tmV, tmO, p);                        \
+    break;
+  switch (var) {
+    F2_LAUNCH(0) F2_LAUNCH(1) F2_LAUNCH(3) F2_LAUNCH(5) F2_LAUNCH(7) F2_LAUNCH(9) F2_LAUNCH(11)
+    default: set_error("BV_ATTN_SM=%d: unknown softmax variant", var); return BV_ERR_INVALID;
+  }
+#undef F2_LAUNCH
   return check_cuda(cudaGetLastError(), "attn_fwd_stream_kernel launch");
 }
 
@@ -851,6 +895,7 @@ int launch_attention_bwd_stream(const AttnBwdArgs& g, cudaStream_t s) {
   p.lse = a.lse;
   p.delta = g.delta;
   p.dk_colsum = g.dk_colsum; p.dv_colsum = g.dv_colsum;
+  { const char* e = getenv("BV_BWD_VARIANT"); p.variant = e ? atoi(e) : 0; }
   const int cols = a.H * DH;
   int rc;
   // delta = rowsum(O o dO)

@@ -17,6 +17,11 @@ def _params(tree):
   return E.FlatParams(specs, [], "cuda", decay_regex=None).init(0)
 
 
+# The applied update is read back as (parameter after - parameter before) in fp32, so it carries the
+# rounding of the fp32 parameter itself (1 ulp of |p| ~ 1e-7 |p|) on top of the update's own.
+RTOL, ATOL = 1e-5, 1.5e-6
+
+
 def _step(tx, state, P, grads):
   """One tx.update with the given gradient tree; returns the applied update per parameter."""
   before = P.numpy_tree("f")
@@ -41,7 +46,7 @@ def test_make_simple():
     sched = sched_fn(step)
     np.testing.assert_almost_equal(sched, 1.0 / total * (total - step))
     for k, v in upd.items():
-      np.testing.assert_allclose(v, -sched * 0.01 * 0.5 * 1.0, rtol=2e-6, atol=1e-9, err_msg=k)
+      np.testing.assert_allclose(v, -sched * 0.01 * 0.5 * 1.0, rtol=RTOL, atol=ATOL, err_msg=k)
 
 
 def test_make_wd():
@@ -57,7 +62,7 @@ def test_make_wd():
     upd, p = _step(tx, state, P, {k: 1.0 for k in P.offsets})
     sched = sched_fn(step)
     for k in upd:
-      np.testing.assert_allclose(upd[k], -sched * (0.01 * 0.5 * 1.0 + p[k] * wds[k]), rtol=3e-6, atol=1e-9, err_msg=k)
+      np.testing.assert_allclose(upd[k], -sched * (0.01 * 0.5 * 1.0 + p[k] * wds[k]), rtol=RTOL, atol=ATOL, err_msg=k)
 
 
 def test_make_clip_norm():
@@ -73,7 +78,7 @@ def test_make_clip_norm():
     upd, _ = _step(tx, state, P, {k: 1.0 for k in P.offsets})
     sched = sched_fn(step)
     for k in upd:
-      np.testing.assert_allclose(upd[k], -sched * 0.01 * 0.5 * factor, rtol=3e-6, atol=1e-9, err_msg=k)
+      np.testing.assert_allclose(upd[k], -sched * 0.01 * 0.5 * factor, rtol=RTOL, atol=ATOL, err_msg=k)
     assert float(state["scalars"][0].sqrt()) == pytest.approx(np.sqrt(3.0), rel=1e-6)
 
 
@@ -101,7 +106,7 @@ def test_make_multi():
     np.testing.assert_almost_equal(fn2(step), mult2 * (total - step) / total)
     for k in vals:
       want = -sched_of[k](step) * (lrb * lr_mults[k] * 0.5 * factor + p[k] * wds[k])
-      np.testing.assert_allclose(upd[k], want, rtol=4e-6, atol=1e-9, err_msg=f"{k} step {step}")
+      np.testing.assert_allclose(upd[k], want, rtol=RTOL, atol=ATOL, err_msg=f"{k} step {step}")
 
 
 def test_frozen_no_state_and_uncovered_params():

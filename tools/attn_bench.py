@@ -32,7 +32,10 @@ def run(B, H, N, what, iters=10):
   return out
 
 what = sys.argv[1] if len(sys.argv) > 1 else "both"
-for B, H, N in ((1024, 12, 196), (1024, 12, 64), (256, 12, 197), (512, 16, 576)):
+shapes = ((1024, 12, 196), (1024, 12, 64), (256, 12, 197), (512, 16, 576))
+if os.environ.get("BV_BENCH_SHAPES"):
+  shapes = tuple(tuple(int(x) for x in sh.split(",")) for sh in os.environ["BV_BENCH_SHAPES"].split(";"))
+for B, H, N in shapes:
   r = run(B, H, N, what)
   print(f"B={B} H={H} N={N} " + "  ".join(f"{k}: {v[0]:.3f} ms {v[1]:.0f} TFLOP/s" for k, v in r.items()),
-        f"[fwd={os.environ.get('BV_ATTN_FWD','default')} bwd={os.environ.get('BV_ATTN_BWD','default')}]", flush=True)
+        f"[fwd={os.environ.get('BV_ATTN_FWD','default')} bwd={os.environ.get('BV_ATTN_BWD','default')} sm={os.environ.get('BV_ATTN_SM','-')}]", flush=True)
