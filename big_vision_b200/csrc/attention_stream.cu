@@ -47,6 +47,20 @@ struct Fwd2Dev {
   float* lse;         // [B, H, Nq] or null
 };
 
+// two exponentials per MUFU operation: exp2 of an fp16 pair (the arguments are <= 0; fp16 keeps them to
+// 2^-11 relative, i.e. the result to <= 0.27 % for p >= 2^-16 and <= 0.07 % for p >= 1/16 -- tighter
+// than the bf16 rounding of P it replaces).  lo -> lower half = lower column.
+__device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
+  uint32_t h, e;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(h));
+  return e;
+}
+__device__ __forceinline__ float f16x2_sum(uint32_t v) {
+  float a, b;
+  asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(a), "=f"(b) : "r"(v));
+  return a + b;
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // three-input max (sm_100)
@@ -58,7 +72,8 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // VAR (tuning switch, BV_ATTN_SM): bit 0 = four independent max / sum chains instead of one serial
 // chain of 128 (each warp scheduler holds only two softmax warps, so a 128-deep dependent chain is
 // pure latency); bit 1 = three-input max; bits 2.. = exponential split: 0 alternate 8-column units
-// between MUFU and the FMA-pipe polynomial, 1 = one unit in four on the polynomial, 2 = all MUFU.
+// between MUFU and the FMA-pipe polynomial, 1 = one unit in four on the polynomial, 2 = all MUFU,
+// 3 = all MUFU as fp16 pairs (ex2.approx.f16x2; P is then an fp16 operand of the P.V product).
 template <bool FULL, int VAR>
 __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, uint32_t sw, int valid,
                                               float scale_log2, uint32_t s_empty_bar, uint32_t p_empty_bar,
@@ -106,6 +121,16 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, u
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     if (UNIT_ON(u)) {
+      if (SPLIT == 3) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint32_t e2 = ex2_f16x2(fmaf(__uint_as_float(sv[u][2 * jj]), scale_log2, -mxs),
+                                        fmaf(__uint_as_float(sv[u][2 * jj + 1]), scale_log2, -mxs));
+          sma[ILP4 ? jj : 0] += f16x2_sum(e2);
+          sv[u][jj] = e2;
+        }
+        continue;
+      }
       float e[8];
       // exp2(scale * s - scale * max), split between MUFU and the FMA-pipe polynomial
       const bool poly = SPLIT == 0 ? (u & 1) : SPLIT == 1 ? ((u & 3) == 3) : false;
@@ -246,7 +271,10 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     } else if (warp == 10) {
       // ================= O_g = P_g V_g issuer =================
-      const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);      // V is MN-major
+      // V is MN-major; P is bf16, or fp16 when the exponentials come out of MUFU as fp16 pairs
+      // (instruction descriptor bits [7,10) = A format: 0 = f16, 1 = bf16)
+      const uint32_t idesc_o = (VAR >> 2) == 3 ? (umma_idesc_bf16(128, DH, 0, 1) & ~(7u << 7))
+                                               : umma_idesc_bf16(128, DH, 0, 1);
       uint32_t g = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int qs = i & 1;
@@ -870,7 +898,7 @@ int launch_attention_fwd_stream(const AttnArgs& a, cudaStream_t s) {
     attn_fwd_stream_kernel<V><<<grid, F2_THREADS, F2_SMEM, s>>>(tmQ, tmK, tmV, tmO, p);                        \
     break;
   switch (var) {
-    F2_LAUNCH(0) F2_LAUNCH(1) F2_LAUNCH(3) F2_LAUNCH(5) F2_LAUNCH(7) F2_LAUNCH(9) F2_LAUNCH(11)
+    F2_LAUNCH(0) F2_LAUNCH(1) F2_LAUNCH(5) F2_LAUNCH(8) F2_LAUNCH(9) F2_LAUNCH(12) F2_LAUNCH(13)
     default: set_error("BV_ATTN_SM=%d: unknown softmax variant", var); return BV_ERR_INVALID;
   }
 #undef F2_LAUNCH
