@@ -53,3 +53,26 @@ def test_ops_refuse_cpu_tensors():
   from big_vision_b200 import ops
   with pytest.raises(L.BvError):
     ops.layernorm_fwd(torch.zeros(4, 64), torch.ones(64), torch.zeros(64))
+
+
+def test_bench_workloads_cover_the_five_baseline_configs():
+  """bench.py --workload: one entry per BASELINE.json config, synthetic batches of the SURVEY 8d shapes."""
+  import importlib.util
+  import json
+  import os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+  bench = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(bench)
+  assert len(json.load(open(os.path.join(root, "BASELINE.json")))["configs"]) == len(bench.WORKLOADS) == 5
+  wl = bench.WORKLOADS["siglip_b16"]
+  b = bench.synthetic_batch(wl, 4, seed=0)
+  assert b["image"].shape == (4, 224, 224, 3) and b["image"].dtype.name == "float32"
+  assert -1.0 <= b["image"].min() and b["image"].max() < 1.0
+  assert b["labels"].shape == (4, 64) and b["labels"].dtype.name == "int32" and (b["labels"][:, -1] == 1).all()
+  assert bench.synthetic_batch(wl, 2, seed=0, uint8=True)["image"].dtype.name == "uint8"
+  c = bench.synthetic_batch(bench.WORKLOADS["vit_b16_cls"], 4, seed=0)
+  assert c["labels"].shape == (4, 1000) and (c["labels"].sum(1) == 1).all()
+  assert bench.WORKLOADS["siglip_l14_336"]["per_gpu_batch"] * 8 == 16384 and wl["per_gpu_batch"] * 8 == 8192
+  model = bench.build_model(bench.WORKLOADS["siglip_l14_336"])
+  assert model.img.scan and model.txt.scan and model.img.width == 1024 and model.img.patch_size == (14, 14)

@@ -149,3 +149,37 @@ def test_param_tree_names_and_shapes_match_reference_layout():
   np_tree = P.numpy_tree("f")
   P2 = model.init(1, common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, device="cpu").load_tree(np_tree)
   assert torch.equal(P.flat, P2.flat)
+
+
+def test_scan_encoder_parameter_tree_matches_reference_scan_layout():
+  """scan=True (models/vit.py:129-148): ONE `encoderblock` sub-tree whose leaves carry a leading depth
+  axis (what vit.pyloop_to_scan produces from the per-layer trees); DenseGeneral shapes keep [d,h,dh]."""
+  from big_vision_b200 import utils as u
+  from big_vision_b200.models import vit
+  kw = dict(width=128, depth=3, mlp_dim=256, num_heads=2, patch_size=(16, 16), pool_type="map")
+  shape = (2, 32, 32, 3)
+  P_loop = vit.Model(None, **kw).init(0, shape, device="cpu")
+  P_scan = vit.Model(None, scan=True, **kw).init(0, shape, device="cpu")
+  flat = P_loop.numpy_tree("f")
+  nested = u.recover_tree(list(flat.keys()), list(flat.values()))
+  want = {k: v.shape for k, v in u.tree_flatten_with_names(vit.pyloop_to_scan(nested))[0]}
+  got = {k: tuple(v.shape) for k, v in P_scan.tree("f").items()}
+  assert got == want
+  blk = "Transformer/encoderblock/"
+  assert got[blk + "MultiHeadDotProductAttention_0/key/kernel"] == (3, 128, 2, 64)
+  assert got[blk + "MultiHeadDotProductAttention_0/out/kernel"] == (3, 2, 64, 128)
+  assert got[blk + "MlpBlock_0/Dense_0/bias"] == (3, 256) and got["MAPHead_0/probe"] == (1, 1, 128)
+  # the decayed group (".*/kernel$") is still one contiguous prefix of the flat buffer
+  assert 0 < P_scan.n_decay < P_scan.total and P_scan.total == P_loop.total
+
+
+def test_mixer_stochastic_depth_schedule_and_masks():
+  """mlp_mixer.py:76: drop_p_i = i / (L - 1) * stoch_depth; masks are 1 - Bernoulli(drop_p_i) per
+  sample and branch (:173-177)."""
+  from big_vision_b200.models import mlp_mixer
+  m = mlp_mixer.Model(10, variant="B/16", stoch_depth=0.1)
+  assert m.drop_p(0) == 0.0 and m.drop_p(11) == pytest.approx(0.1) and m.drop_p(5) == pytest.approx(0.1 * 5 / 11)
+  masks = m.draw_masks(np.random.default_rng(0), 4096, "cpu")
+  assert tuple(masks.shape) == (12, 2, 4096) and set(np.unique(masks.numpy())) <= {0.0, 1.0}
+  assert float(masks[0].min()) == 1.0
+  assert abs(float(1 - masks[11].mean()) - 0.1) < 0.02

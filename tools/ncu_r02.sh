@@ -6,6 +6,10 @@ mkdir -p gpurun_out/ncu
 B="python bench.py --steps 2 --warmup 3 --per-gpu-batch 256 --no-cpu-baseline --no-gpu-baseline"
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   -c 8000 --csv --log-file gpurun_out/ncu/launches_siglip_b16_n256.csv $B > gpurun_out/ncu/launches.log 2>&1
+# the GEMM launches of the full-size default bench (1024 pairs): DRAM traffic per launch for roofline.traffic
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  -k regex:gemm_kernel -s 933 -c 622 --csv --log-file gpurun_out/ncu/launches_siglip_b16_n1024_gemm.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/ncu/launches_gemm.log 2>&1
 cap() {  # name regex skip [command]
   local cmd="${4:-$B}"
   timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
