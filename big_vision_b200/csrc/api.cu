@@ -164,6 +164,12 @@ int bv_siglip_loss(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t 
   return launch_siglip_loss_ew(dots, n, B, ld, row_offset, t_param, b_param, global_B, G, ldg,
                                loss, dt, db, partials_ws, S(stream));
 }
+int bv_softmax_contrastive_loss(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
+                                const float* t_param, int64_t global_B, float weight, void* G, int64_t ldg,
+                                float* loss, float* dt, float* ncorrect, float* rows_ws, void* stream) {
+  return launch_softmax_contrastive(dots, n, B, ld, row_offset, t_param, global_B, weight, G, ldg, loss, dt,
+                                    ncorrect, rows_ws, S(stream));
+}
 int bv_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
                     float* row_loss_ws, int64_t n, int32_t C, void* stream) {
   return launch_sigmoid_xent(logits, labels, loss, dlogits, row_loss_ws, n, C, S(stream));

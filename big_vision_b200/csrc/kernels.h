@@ -104,6 +104,9 @@ int launch_siglip_loss_ew(const float* dots, int64_t n, int64_t B, int64_t ld, i
                           const float* t_param, const float* b_param, int64_t global_B, void* G,
                           int64_t ldg, float* loss, float* dt, float* db, float* partials,
                           cudaStream_t s);
+int launch_softmax_contrastive(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
+                               const float* t_param, int64_t global_B, float weight, void* G, int64_t ldg,
+                               float* loss, float* dt, float* ncorrect, float* rows_ws, cudaStream_t s);
 int launch_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,
                         float* row_loss, int64_t n, int C, cudaStream_t s);
 int launch_softmax_xent(const float* logits, const float* labels, float* loss, float* dlogits,

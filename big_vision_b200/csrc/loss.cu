@@ -109,6 +109,54 @@ finish_sums_kernel(const float* __restrict__ part, int64_t count, float* out0, f
   }
 }
 
+// One direction of the softmax (CLIP) contrastive loss, _deprecated_contrastive.py:80-101:
+//   x_ij = dots_ij * exp(t'),  loss_i = logsumexp_j x_ij - x_i,pos(i),  pos(i) = row_offset + i
+//   loss += weight/global_B * sum_i loss_i ;  G_ij = weight/global_B * (softmax_ij - [j == pos]) * exp(t')
+//   dt'  += sum_ij (G_ij / exp(t')) * x_ij ;  ncorrect += #[argmax_j x_ij == pos(i)]   (first max wins)
+// One warp per row; per-row partials (loss, dt', correct) go to `rows_ws` [3, n] and are summed in a
+// fixed order by finish_sums_kernel (deterministic like the other losses).
+__global__ void __launch_bounds__(256)
+softmax_contrastive_kernel(const float* __restrict__ dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
+                           const float* __restrict__ t_param, float scale, bf16* __restrict__ G, int64_t ldg,
+                           float* __restrict__ rows_ws) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float t = __expf(t_param[0]);
+  const float* d = dots + row * ld;
+  const int64_t pos = row_offset + row;
+  float mx = -INFINITY;
+  int64_t arg = 0;
+  for (int64_t c = lane; c < B; c += 32) {
+    const float x = d[c] * t;
+    if (x > mx) { mx = x; arg = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int64_t oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+  }
+  float se = 0.f;
+  for (int64_t c = lane; c < B; c += 32) se += __expf(d[c] * t - mx);
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  float dt_acc = 0.f;
+  for (int64_t c = lane; c < B; c += 32) {
+    const float x = d[c] * t;
+    const float gx = (__expf(x - lse) - (c == pos ? 1.f : 0.f)) * scale;     // d loss / d x
+    dt_acc += gx * x;
+    G[row * ldg + c] = __float2bfloat16_rn(gx * t);                            // d loss / d dot
+  }
+  dt_acc = warp_sum(dt_acc);
+  if (lane == 0) {
+    const float xpos = (pos >= 0 && pos < B) ? d[pos] * t : 0.f;
+    rows_ws[row] = (lse - xpos) * scale;
+    rows_ws[n + row] = dt_acc;
+    rows_ws[2 * n + row] = (arg == pos) ? 1.f : 0.f;
+  }
+}
+
 // one warp per row
 __global__ void __launch_bounds__(256)
 sigmoid_xent_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
@@ -181,6 +229,22 @@ int launch_siglip_loss_ew(const float* dots, int64_t n, int64_t B, int64_t ld, i
   int rc = check_cuda(cudaGetLastError(), "siglip_loss_kernel launch");
   if (rc || partials == nullptr) return rc;
   finish_sums_kernel<<<1, 256, 0, s>>>(partials, blocks, loss, dt, db);
+  return check_cuda(cudaGetLastError(), "finish_sums_kernel launch");
+}
+
+int launch_softmax_contrastive(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
+                               const float* t_param, int64_t global_B, float weight, void* G, int64_t ldg,
+                               float* loss, float* dt, float* ncorrect, float* rows_ws, cudaStream_t s) {
+  if (n <= 0 || B <= 0 || global_B <= 0 || rows_ws == nullptr) {
+    set_error("bv_softmax_contrastive_loss: need n, B > 0 and the [3, n] workspace");
+    return BV_ERR_INVALID;
+  }
+  softmax_contrastive_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(
+      dots, n, B, ld, row_offset, t_param, weight / static_cast<float>(global_B), reinterpret_cast<bf16*>(G), ldg,
+      rows_ws);
+  int rc = check_cuda(cudaGetLastError(), "softmax_contrastive_kernel launch");
+  if (rc) return rc;
+  finish_sums_kernel<<<1, 256, 0, s>>>(rows_ws, n, loss, dt, ncorrect);
   return check_cuda(cudaGetLastError(), "finish_sums_kernel launch");
 }
 

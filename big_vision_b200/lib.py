@@ -90,6 +90,8 @@ SIGNATURES = {
     "bv_drop_cls": [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "bv_siglip_loss": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp,
                        c_vp, c_vp, c_vp],
+    "bv_softmax_contrastive_loss": [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_f32, c_vp, c_i64, c_vp, c_vp,
+                                    c_vp, c_vp, c_vp],
     "bv_sigmoid_xent": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
     "bv_softmax_xent": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp],
     "bv_adam_step": [ctypes.POINTER(AdamArgs), c_vp],
@@ -138,7 +140,7 @@ def check(rc, what):
 # kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
 LAUNCHES = [0]
 _LAUNCHES_PER_CALL = {"bv_embed_bwd": 2, "bv_retrieval_ranks": 2, "bv_siglip_loss": 2,
-                      "bv_sigmoid_xent": 2, "bv_softmax_xent": 2, "bv_adafactor_step": 4}
+                      "bv_sigmoid_xent": 2, "bv_softmax_xent": 2, "bv_softmax_contrastive_loss": 2, "bv_adafactor_step": 4}
 LOSS_WS_FLOATS = 8192      # BV_LOSS_WS_FLOATS
 
 

@@ -340,6 +340,16 @@ def siglip_loss(dots, row_offset, t_param, b_param, global_b, loss, dt, db):
   return G
 
 
+def softmax_contrastive_loss(dots, row_offset, t_param, global_b, weight, loss, dt, ncorrect):
+  """One direction of the CLIP softmax loss on dots [n, B]; returns G (bf16) = d loss / d dots."""
+  n, B = dots.shape
+  G = torch.empty((n, B), dtype=torch.bfloat16, device=dots.device)
+  ws = torch.empty(3 * n, dtype=torch.float32, device=dots.device)
+  L.call("bv_softmax_contrastive_loss", _p(dots), n, B, dots.stride(0), row_offset, _p(t_param), global_b,
+         float(weight), _p(G), G.stride(0), _p(loss), _p(dt), _p(ncorrect), _p(ws), _stream())
+  return G
+
+
 def sigmoid_xent(logits, labels, loss, want_grad=True):
   n, C = logits.shape
   dl = torch.empty_like(logits) if want_grad else None

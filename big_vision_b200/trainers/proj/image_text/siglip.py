@@ -203,7 +203,41 @@ def chunked_sigmoid_loss_fwd_bwd(P, zimg, ztxt, d, scal):
   return dzimg, dztxt
 
 
-_LOSS_FNS = {"sigmoid": sigmoid_loss_fwd_bwd, "chunked_sigmoid": chunked_sigmoid_loss_fwd_bwd}
+def softmax_loss_fwd_bwd(P, zimg, ztxt, d, scal):
+  """The CLIP softmax loss, `softmax_loss` of _deprecated_contrastive.py:80-101 (config.loss_fn="softmax"):
+  0.5 * (image->text + text->image) InfoNCE, each direction a softmax of the local rows against ALL
+  gathered columns with the positive on this rank's diagonal block; temperature only (no bias).
+  Global semantics: mean over the global batch of both directions (the reference's per-device means
+  followed by pmean).  scal[0] += loss share, scal[1] / scal[2] += number of correct i2t / t2i
+  retrievals on this rank (the reference's `i2t_acc` / `t2i_acc` times n).
+  Same arguments and return values as sigmoid_loss_fwd_bwd."""
+  n, D = zimg.shape
+  zimg_all = d.all_gather_rows(zimg)                       # t2i needs the gathered image embeddings too
+  ztxt_all = d.all_gather_rows(ztxt)
+  B = ztxt_all.shape[0]
+  cast16 = lambda x: ops.cast(x, torch.empty_like(x, dtype=torch.bfloat16))
+  zi16, zt16, zia16, zta16 = cast16(zimg), cast16(ztxt), cast16(zimg_all), cast16(ztxt_all)
+  off = d.rank * n
+  # image -> text: local images against all texts
+  dots = ops.gemm(zi16, zta16, out_dtype=torch.float32)                          # [n, B]
+  G1 = ops.softmax_contrastive_loss(dots, off, P.f("t"), B, 0.5, scal[0:1], P.g("t"), scal[1:2])
+  # text -> image: local texts against all images
+  dots = ops.gemm(zt16, zia16, out_dtype=torch.float32)                          # [n, B]
+  G2 = ops.softmax_contrastive_loss(dots, off, P.f("t"), B, 0.5, scal[0:1], P.g("t"), scal[2:3])
+  dzimg = ops.gemm(G1, zta16, b_mn=True, out_dtype=torch.float32)                # G1 . ztxt_all
+  dztxt = ops.gemm(G2, zia16, b_mn=True, out_dtype=torch.float32)                # G2 . zimg_all
+  # contributions to the OTHER ranks' rows (the gathered operand of each direction), summed back
+  dztxt_all = ops.gemm(G1, zi16, a_mn=True, b_mn=True, out_dtype=torch.float32)  # G1^T . zimg   [B, D]
+  dzimg_all = ops.gemm(G2, zt16, a_mn=True, b_mn=True, out_dtype=torch.float32)  # G2^T . ztxt   [B, D]
+  dztxt = ops.axpby(dztxt, d.reduce_scatter_rows(dztxt_all), 1.0, 1.0) if d.world > 1 else \
+      ops.axpby(dztxt, dztxt_all, 1.0, 1.0)
+  dzimg = ops.axpby(dzimg, d.reduce_scatter_rows(dzimg_all), 1.0, 1.0) if d.world > 1 else \
+      ops.axpby(dzimg, dzimg_all, 1.0, 1.0)
+  return dzimg, dztxt
+
+
+_LOSS_FNS = {"sigmoid": sigmoid_loss_fwd_bwd, "chunked_sigmoid": chunked_sigmoid_loss_fwd_bwd,
+             "softmax": softmax_loss_fwd_bwd}
 
 
 def _loss_fn(config):

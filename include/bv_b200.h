@@ -208,6 +208,15 @@ int bv_siglip_loss(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t 
                    const float* t_param, const float* b_param, int64_t global_B, void* G,
                    int64_t ldg, float* loss, float* dt, float* db, float* partials_ws,
                    void* stream);
+/* One direction of the softmax (CLIP) contrastive loss, `softmax_loss` of
+ * trainers/proj/image_text/_deprecated_contrastive.py:80-101, on a slab dots[n,B] = z1_local . z2_all^T:
+ *   x = dots * exp(t'); loss += weight/global_B * sum_i (logsumexp_j x_ij - x_i,pos(i)), pos(i) = row_offset+i;
+ *   G[n,B] (bf16) = d loss / d dots; dt += d loss / d t'; ncorrect += #(argmax_j x_ij == pos(i)).
+ * rows_ws: [3, n] floats (per-row partials, summed in a fixed order: deterministic).  The trainer
+ * calls it once per direction (i2t, t2i) with weight 0.5. */
+int bv_softmax_contrastive_loss(const float* dots, int64_t n, int64_t B, int64_t ld, int64_t row_offset,
+                                const float* t_param, int64_t global_B, float weight, void* G, int64_t ldg,
+                                float* loss, float* dt, float* ncorrect, float* rows_ws, void* stream);
 /* utils.py:236-243 / 276-281 : mean over n rows; loss is accumulated; dlogits may be NULL.
  * row_loss_ws: NULL = atomics; [n] floats = per-row losses + fixed-order sum (deterministic). */
 int bv_sigmoid_xent(const float* logits, const float* labels, float* loss, float* dlogits,

@@ -248,6 +248,18 @@ def siglip_loss_per_device(zimg, ztxt, t, b, world):
   return total / world
 
 
+def softmax_contrastive_loss(zimg, ztxt, t):
+  """`softmax_loss` (CLIP), trainers/proj/image_text/_deprecated_contrastive.py:80-101, on the GLOBAL
+  batch: 0.5 * (mean_i -log_softmax(zimg ztxt^T t, axis=1)_ii + mean_i -log_softmax(..., axis=0)_ii);
+  also the two retrieval accuracies (argmax == diagonal, :89).  t is exp(t')."""
+  logits = zimg @ ztxt.T * t
+  idx = torch.arange(logits.shape[0])
+  l1 = -(torch.log_softmax(logits, dim=1)[idx, idx]).mean()
+  l2 = -(torch.log_softmax(logits, dim=0)[idx, idx]).mean()
+  acc = ((logits.argmax(1) == idx).double().mean(), (logits.argmax(0) == idx).double().mean())
+  return 0.5 * (l1 + l2), acc
+
+
 def sigmoid_xent(logits, labels):
   """utils.py:236-243."""
   log_p = torch.nn.functional.logsigmoid(logits)

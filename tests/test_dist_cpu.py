@@ -58,7 +58,24 @@ def _worker(rank, world, port, ret, loss_fn="sigmoid"):
     db += b.grad.float()
     return d.grad.float()
 
+  def softmax_contrastive_loss(dots, row_offset, t_param, global_b, weight, loss, dt, ncorrect):
+    d = dots.double().requires_grad_(True)
+    t = t_param.double().requires_grad_(True)
+    n = d.shape[0]
+    x = d * t.exp()
+    idx = torch.arange(n)
+    l = weight * (torch.logsumexp(x, 1) - x[idx, row_offset + idx]).sum() / global_b
+    l.backward()
+    loss += l.detach().float()
+    dt += t.grad.float()
+    ncorrect += float((x.argmax(1) == row_offset + idx).sum())
+    return d.grad.float()
+
+  def axpby(x, y, a=1.0, b=1.0, out=None):
+    return a * x + b * y
+
   ops.cast, ops.gemm, ops.siglip_loss = cast, gemm, siglip_loss
+  ops.softmax_contrastive_loss, ops.axpby = softmax_contrastive_loss, axpby
 
   class FakeP:
     offsets = {"t": 0, "b": 1}
@@ -84,8 +101,12 @@ def _worker(rank, world, port, ret, loss_fn="sigmoid"):
   zir, ztr = zi.clone().requires_grad_(True), zt.clone().requires_grad_(True)
   tr = torch.tensor(math.log(10.0), dtype=torch.float64, requires_grad=True)
   br = torch.tensor(-10.0, dtype=torch.float64, requires_grad=True)
-  l = O.siglip_loss(zir, ztr, tr.exp(), br)
-  l.backward()
+  if loss_fn == "softmax":
+    l, _ = O.softmax_contrastive_loss(zir, ztr, tr.exp())
+    (l + 0.0 * br).backward()
+  else:
+    l = O.siglip_loss(zir, ztr, tr.exp(), br)
+    l.backward()
   errs = {
       "loss": abs(float(scal[0]) - float(l.detach())),
       "dzimg": float((dzimg.double() - zir.grad[rank * n:(rank + 1) * n]).abs().max()),
@@ -98,12 +119,12 @@ def _worker(rank, world, port, ret, loss_fn="sigmoid"):
 
 
 @pytest.mark.parametrize("world,loss_fn", [(2, "sigmoid"), (3, "sigmoid"), (2, "chunked_sigmoid"),
-                                           (3, "chunked_sigmoid")])
+                                           (3, "chunked_sigmoid"), (2, "softmax"), (3, "softmax")])
 def test_sharded_sigmoid_loss_equals_global_loss(world, loss_fn):
   """Both DP forms of the loss -- all-gather ([n,B] slab) and the paper's chunked rounds ([n,n]
   blocks, broadcast from / reduce to the chunk's owner) -- reproduce the global-batch loss and
   gradients (SURVEY 8e invariant)."""
-  port = 29500 + os.getpid() % 1000 + world + (10 if loss_fn != "sigmoid" else 0)
+  port = 29500 + os.getpid() % 1000 + world + {"sigmoid": 0, "chunked_sigmoid": 10, "softmax": 20}[loss_fn]
   ctx = mp.get_context("spawn")
   ret = ctx.Manager().dict()
   procs = [ctx.Process(target=_worker, args=(r, world, port, ret, loss_fn)) for r in range(world)]

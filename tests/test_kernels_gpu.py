@@ -255,6 +255,28 @@ def test_siglip_loss_slab(ops, n, B, off):
   _close(db, br.grad, 1e-4)
 
 
+@pytest.mark.parametrize("n,B,off", [(8, 8, 0), (64, 256, 128), (33, 100, 7)])
+def test_softmax_contrastive_slab(ops, n, B, off):
+  """One direction of the CLIP softmax loss (_deprecated_contrastive.py:80-101) on a rank's [n, B]
+  slab: loss, d loss / d dots, d loss / d t', and the argmax == positive count (integer, exact)."""
+  g = torch.Generator().manual_seed(n + B)
+  dots = torch.randn(n, B, generator=g) * 0.3
+  dots[torch.arange(n), off + torch.arange(n)] += 0.4 * (torch.arange(n) % 3 == 0)   # some correct retrievals
+  tp = torch.tensor([math.log(10.0)])
+  dr, tr = dots.double().requires_grad_(True), tp.double().requires_grad_(True)
+  x = dr * tr.exp()
+  idx = torch.arange(n)
+  ref = 0.5 * (torch.logsumexp(x, 1) - x[idx, off + idx]).sum() / B
+  ref.backward()
+  sc = torch.zeros(3, device="cuda")
+  dt = torch.zeros(1, device="cuda")
+  G = ops.softmax_contrastive_loss(dots.cuda(), off, tp.cuda(), B, 0.5, sc[0:1], dt, sc[1:2])
+  _close(sc[0:1], ref.detach().reshape(1), 1e-5)
+  _close(G, dr.grad, 2 ** -7)
+  _close(dt, tr.grad.reshape(1), 1e-4)
+  assert int(sc[1]) == int((x.argmax(1) == off + idx).sum())
+
+
 def test_classification_losses(ops):
   g = torch.Generator().manual_seed(11)
   lg = torch.randn(37, 1000, generator=g) * 3

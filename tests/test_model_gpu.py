@@ -68,6 +68,30 @@ def test_loss_and_gradients_match_golden(tiny):
   assert not bad, f"gradient mismatch (abs err, tol): {sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]}"
 
 
+def test_softmax_clip_loss_and_gradients_match_oracle(tiny):
+  """config.loss_fn="softmax" (_deprecated_contrastive.py:80-101, 322-331): bidirectional InfoNCE
+  through both towers against autograd through the fp64 oracle."""
+  from big_vision_b200.trainers.proj.image_text import siglip
+  model, P, image, text, z, tree = tiny
+  loss, aux = siglip.loss_and_grads(model, P, image, text, loss_fn="softmax")
+  p64 = O.to_f64_tree(tree, requires_grad=True)
+  zi, zt, ex = O.two_towers_forward(p64, image.cpu(), text.cpu(), common.oracle_cfg(common.TINY), "float32")
+  ref, acc = O.softmax_contrastive_loss(zi, zt, ex["t"])
+  ref.backward()
+  assert float(loss) == pytest.approx(float(ref), rel=5e-3)
+  grads = P.numpy_tree("g")
+  gmax = max(float(v.grad.abs().max()) for v in p64.values() if v.grad is not None)
+  bad = {}
+  for k, g in grads.items():
+    r = p64[k].grad.numpy() if p64[k].grad is not None else np.zeros_like(g)
+    err = float(np.abs(g.astype(np.float64) - r).max())
+    tol = 6e-2 * float(np.abs(r).max()) + 3e-3 * gmax
+    if err > tol:
+      bad[k] = (err, tol)
+  assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]
+  assert float(np.abs(grads["b"]).max()) == 0.0          # the softmax loss has no bias term
+
+
 def test_loss_gradient_is_consistent_with_finite_difference(tiny):
   """d loss / d t' and d loss / d b from the kernels vs a central difference of the kernel loss."""
   from big_vision_b200.trainers.proj.image_text import siglip

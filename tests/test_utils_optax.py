@@ -121,10 +121,11 @@ def test_get_mixup_draws_a_at_least_one_half():
 
 
 def test_siglip_loss_fn_selection():
-  """config.loss_fn as in _deprecated_contrastive.py:322-331; the softmax (CLIP) loss is not built."""
+  """config.loss_fn as in _deprecated_contrastive.py:322-331; "softmax" is the CLIP loss of :80-101."""
   import pytest
   from big_vision_b200.trainers.proj.image_text import siglip
   assert siglip._loss_fn(None) is siglip.sigmoid_loss_fwd_bwd
   assert siglip._loss_fn({"loss_fn": "chunked_sigmoid"}) is siglip.chunked_sigmoid_loss_fwd_bwd
+  assert siglip._loss_fn({"loss_fn": "softmax"}) is siglip.softmax_loss_fwd_bwd
   with pytest.raises(NotImplementedError):
-    siglip._loss_fn({"loss_fn": "softmax"})
+    siglip._loss_fn({"loss_fn": "hinge"})
