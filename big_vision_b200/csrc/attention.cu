@@ -127,13 +127,22 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       if (UNIT_ON(u)) {
+        if (u * 8 + 8 <= valid) {
+          // every column of this unit is a real key (warp-uniform test): no per-element masking
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float sc = __uint_as_float(sv[u][j]);
-          if (u * 8 + j >= valid) sc = -INFINITY;     // padded key columns
-          sv[u][j] = __float_as_uint(sc);
-          float& m = mxa[ILP ? (j & 3) : 0];
-          m = fmaxf(m, sc);
+          for (int j = 0; j < 8; ++j) {
+            float& m = mxa[ILP ? (j & 3) : 0];
+            m = fmaxf(m, __uint_as_float(sv[u][j]));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float sc = __uint_as_float(sv[u][j]);
+            if (u * 8 + j >= valid) sc = -INFINITY;     // padded key columns
+            sv[u][j] = __float_as_uint(sc);
+            float& m = mxa[ILP ? (j & 3) : 0];
+            m = fmaxf(m, sc);
+          }
         }
       }
     }
