@@ -74,7 +74,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // pure latency); bit 1 = three-input max; bits 2.. = exponential split: 0 alternate 8-column units
 // between MUFU and the FMA-pipe polynomial, 1 = one unit in four on the polynomial, 2 = all MUFU,
 // 3 = all MUFU as fp16 pairs (ex2.approx.f16x2; P is then an fp16 operand of the P.V product).
-template <bool FULL, int VAR>
+template <bool FULL, int VAR, bool TSP>
 __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, uint32_t sw, int valid,
                                               float scale_log2, uint32_t s_empty_bar, uint32_t p_empty_bar,
                                               uint32_t p_empty_parity, float& mxs_out, float& sum_out) {
@@ -154,13 +154,33 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, u
   const float sum = (sma[0] + sma[1]) + (sma[2] + sma[3]);
   // the P buffer is free once the P.V product of this warpgroup's previous block has retired
   mbar_wait(p_empty_bar, p_empty_parity);
+  if (TSP) {
+    // P stays in tensor memory (operand A of the P.V product): unit u = packed columns 4u..4u+3 of the
+    // P region that follows this warpgroup's S region; `p_row` carries that TMEM address here
+    tc_fence_after();
 #pragma unroll
-  for (int u = 0; u < 16; ++u) {
-    if (UNIT_ON(u)) {
-      const uint32_t k = static_cast<uint32_t>(u);
-      const uint32_t addr = p_row + (k >> 3) * TILE_BYTES + (((k & 7u) ^ sw) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sv[u][0]),
-                   "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
+    for (int g = 0; g < 4; ++g) {
+      if (FULL || g * 4 < nunits) {
+        uint32_t w16[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          w16[q * 4 + 0] = sv[g * 4 + q][0]; w16[q * 4 + 1] = sv[g * 4 + q][1];
+          w16[q * 4 + 2] = sv[g * 4 + q][2]; w16[q * 4 + 3] = sv[g * 4 + q][3];
+        }
+        tmem_st_32x32b_x16(p_row + g * 16, w16);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  } else {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (UNIT_ON(u)) {
+        const uint32_t k = static_cast<uint32_t>(u);
+        const uint32_t addr = p_row + (k >> 3) * TILE_BYTES + (((k & 7u) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(sv[u][0]),
+                     "r"(sv[u][1]), "r"(sv[u][2]), "r"(sv[u][3]) : "memory");
+      }
     }
   }
 #undef UNIT_ON
@@ -168,7 +188,10 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t p_row, u
   sum_out = sum;
 }
 
-template <int VAR>
+// TSP: P stays in tensor memory (tcgen05.st, A operand of the P.V product read from TMEM): no 32 KB
+// store + 32 KB MMA read of P per block through shared memory.  TMEM then holds S_w | P_w at w * 192
+// (128 + 64 columns) and ONE O accumulator per warpgroup at 384 + w * 64.
+template <int VAR, bool TSP>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -215,7 +238,12 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  constexpr uint32_t O_COL0 = 256;
+  // TMEM columns and the O / statistics buffer of warpgroup w's n-th block
+  auto s_col = [](uint32_t w) { return TSP ? w * 192u : w * 128u; };
+  auto p_col = [](uint32_t w) { return w * 192u + 128u; };                       // TSP only
+  auto o_col = [](uint32_t w, uint32_t ob) { return TSP ? 384u + w * 64u : 256u + (2u * w + ob) * 64u; };
+  auto OB = [](uint32_t n) { return TSP ? 0u : (n & 1u); };                       // buffer index
+  auto OPH = [](uint32_t n) { return TSP ? (n & 1u) : ((n >> 1) & 1u); };         // parity of this use
 
   const int my_tiles = (p.tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                        static_cast<int>(gridDim.x);
@@ -260,7 +288,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           mbar_wait(s_empty(w), ((g >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint64_t dk = umma_smem_desc_sw128(base + F2_KV_OFF + st * 2 * TILE_BYTES, 16, 1024);
-          const uint32_t d = tmem_base + w * BK;
+          const uint32_t d = tmem_base + s_col(w);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(d, dq + k * 2, dk + k * 2, idesc_s, k > 0 ? 1u : 0u);
@@ -279,21 +307,24 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int i = 0; i < my_tiles; ++i) {
         const int qs = i & 1;
         for (int j = 0; j < NB; ++j, ++g) {
-          const uint32_t w = g & 1u, st = g % F2_NST, n = g >> 1, ob = n & 1u;
+          const uint32_t w = g & 1u, st = g % F2_NST, n = g >> 1, ob = OB(n);
           int valid = p.Nk - j * BK;
           if (valid > BK) valid = BK;
           const int ksteps = (valid + 15) >> 4;
           mbar_wait(p_full(w), n & 1u);
           mbar_wait(kv_full(st), (g / F2_NST) & 1u);
-          mbar_wait(o_empty(w, ob), ((n >> 1) & 1u) ^ 1u);
+          mbar_wait(o_empty(w, ob), OPH(n) ^ 1u);
           tc_fence_after();
           const uint64_t dpd = umma_smem_desc_sw128(base + F2_P_OFF + w * 2 * TILE_BYTES, 16, 1024);
           const uint64_t dvd = umma_smem_desc_sw128(base + F2_KV_OFF + st * 2 * TILE_BYTES + TILE_BYTES, 8192, 1024);
-          const uint32_t d = tmem_base + O_COL0 + (2 * w + ob) * DH;
+          const uint32_t d = tmem_base + o_col(w, ob);
+          const uint32_t pt = tmem_base + p_col(w);
           if (elect_one()) {
-            for (int kk = 0; kk < ksteps; ++kk)
-              umma_bf16_ss(d, dpd + (kk >> 2) * (TILE_BYTES / 16) + (kk & 3) * 2, dvd + kk * 128, idesc_o,
-                           kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              if (TSP) umma_bf16_ts(d, pt + kk * 8, dvd + kk * 128, idesc_o, kk > 0 ? 1u : 0u);
+              else umma_bf16_ss(d, dpd + (kk >> 2) * (TILE_BYTES / 16) + (kk & 3) * 2, dvd + kk * 128, idesc_o,
+                                kk > 0 ? 1u : 0u);
+            }
             umma_commit(o_full(w, ob));
             umma_commit(p_empty(w));
             umma_commit(kv_empty(st));       // K_g was consumed by S_g before softmax could finish P_g
@@ -326,16 +357,16 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int c = 0; c < DH; ++c) acc[c] = 0.f;
       float M = -INFINITY, Lsum = 0.f;
       for (int j = 0; j < NB; ++j, ++g) {
-        const uint32_t w = g & 1u, n = g >> 1, ob = n & 1u;
-        mbar_wait(o_full(w, ob), (n >> 1) & 1u);
-        mbar_wait(st_full(w, ob), (n >> 1) & 1u);
+        const uint32_t w = g & 1u, n = g >> 1, ob = OB(n);
+        mbar_wait(o_full(w, ob), OPH(n));
+        mbar_wait(st_full(w, ob), OPH(n));
         tc_fence_after();
         if (active) {
           const float* st = stats + ((2 * w + ob) * 2) * 128;
           const float mb = st[row], lb = st[128 + row];
           const float Mn = fmaxf(M, mb);
           const float fa = ex2_mufu(M - Mn), fb = ex2_mufu(mb - Mn);
-          const uint32_t o_addr = tmem_base + lane_addr + O_COL0 + (2 * w + ob) * DH;
+          const uint32_t o_addr = tmem_base + lane_addr + o_col(w, ob);
 #pragma unroll
           for (int c = 0; c < DH / 16; ++c) {
             uint32_t ov[16];
@@ -386,8 +417,8 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int row = quarter * 32 + lane;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_addr + w * BK;
-    const uint32_t p_row = base + F2_P_OFF + w * 2 * TILE_BYTES + row * 128;
+    const uint32_t s_addr = tmem_base + lane_addr + s_col(w);
+    const uint32_t p_row = TSP ? tmem_base + lane_addr + p_col(w) : base + F2_P_OFF + w * 2 * TILE_BYTES + row * 128;
     const float scale_log2 = pin_reg(p.scale_log2);
     const int pQT = pin_reg(p.QT), pNq = pin_reg(p.Nq), pNk = pin_reg(p.Nk);
     const uint32_t b_s_full = s_full(w), b_s_empty = s_empty(w), b_p_full = p_full(w), b_p_empty = p_empty(w);
@@ -398,7 +429,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const bool active = quarter * 32 < pNq - qt * TQ;
       for (int j = 0; j < NB; ++j, ++g) {
         if ((g & 1u) != static_cast<uint32_t>(w)) continue;
-        const uint32_t n = g >> 1, ob = n & 1u;
+        const uint32_t n = g >> 1, ob = OB(n);
         int valid = pNk - j * BK;
         mbar_wait(b_s_full, n & 1u);
         tc_fence_after();
@@ -409,19 +440,19 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(b_s_empty);
           mbar_wait(b_p_empty, (n & 1u) ^ 1u);
-          mbar_wait(o_empty(w, ob), ((n >> 1) & 1u) ^ 1u);
+          mbar_wait(o_empty(w, ob), OPH(n) ^ 1u);
           __syncwarp();
           if (lane == 0) { mbar_arrive(b_p_full); mbar_arrive(st_full(w, ob)); }
           continue;
         }
         float mxs, sum;
         if (valid >= BK)
-          softmax_block<true, VAR>(s_addr, p_row, sw, BK, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
+          softmax_block<true, VAR, TSP>(s_addr, p_row, sw, BK, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
         else
-          softmax_block<false, VAR>(s_addr, p_row, sw, valid, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
+          softmax_block<false, VAR, TSP>(s_addr, p_row, sw, valid, scale_log2, b_s_empty, b_p_empty, (n & 1u) ^ 1u, mxs, sum);
         // statistics of this block for the epilogue; the slot is free once the epilogue has consumed
         // the previous block that used this (w, ob) buffer pair
-        mbar_wait(o_empty(w, ob), ((n >> 1) & 1u) ^ 1u);
+        mbar_wait(o_empty(w, ob), OPH(n) ^ 1u);
         {
           float* st = stats + ((2 * w + ob) * 2) * 128;
           st[row] = mxs;
@@ -890,15 +921,17 @@ int launch_attention_fwd_stream(const AttnArgs& a, cudaStream_t s) {
   const int grid = p.tiles < sms ? p.tiles : sms;
   int var = F2_DEFAULT_VAR;
   { const char* e = getenv("BV_ATTN_SM"); if (e) var = atoi(e); }
-#define F2_LAUNCH(V)                                                                                           \
-  case V:                                                                                                      \
-    rc = check_cuda(cudaFuncSetAttribute(attn_fwd_stream_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         F2_SMEM), "cudaFuncSetAttribute(attn_fwd_stream)");                    \
-    if (rc) return rc;                                                                                         \
-    attn_fwd_stream_kernel<V><<<grid, F2_THREADS, F2_SMEM, s>>>(tmQ, tmK, tmV, tmO, p);                        \
+  // BV_ATTN_SM + 100 selects the variant with P kept in tensor memory (TSP)
+#define F2_LAUNCH(V, T)                                                                                         \
+  case V + (T ? 100 : 0):                                                                                       \
+    rc = check_cuda(cudaFuncSetAttribute(attn_fwd_stream_kernel<V, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         F2_SMEM), "cudaFuncSetAttribute(attn_fwd_stream)");                     \
+    if (rc) return rc;                                                                                          \
+    attn_fwd_stream_kernel<V, T><<<grid, F2_THREADS, F2_SMEM, s>>>(tmQ, tmK, tmV, tmO, p);                      \
     break;
   switch (var) {
-    F2_LAUNCH(0) F2_LAUNCH(1) F2_LAUNCH(5) F2_LAUNCH(8) F2_LAUNCH(9) F2_LAUNCH(12) F2_LAUNCH(13)
+    F2_LAUNCH(0, false) F2_LAUNCH(5, false) F2_LAUNCH(8, false) F2_LAUNCH(9, false) F2_LAUNCH(12, false)
+    F2_LAUNCH(8, true) F2_LAUNCH(9, true) F2_LAUNCH(12, true)
     default: set_error("BV_ATTN_SM=%d: unknown softmax variant", var); return BV_ERR_INVALID;
   }
 #undef F2_LAUNCH

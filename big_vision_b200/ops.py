@@ -175,6 +175,8 @@ def attention_bwd(do, q, k, v, o, lse, heads, scale=None, dq=None, dk=None, dv=N
                        delta=delta.data_ptr() if delta is not None else None,
                        dq_accum=dq_accum.data_ptr() if dq_accum is not None else None)
   L.call("bv_attention_bwd", ctypes.byref(args), _stream())
+  if delta is not None and (Nq > 256 or k.shape[1] > 256 or os.environ.get("BV_ATTN_BWD", "")[:1] == "s"):
+    L.LAUNCHES[0] += 2          # streaming path = delta pre-kernel + main kernel + dQ conversion
   return dq, dk, dv
 
 

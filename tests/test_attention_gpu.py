@@ -57,6 +57,27 @@ def test_stream_forward(ops, monkeypatch, B, H, Nq, Nk):
   _close(lse, lse_ref, 1e-5)
 
 
+@pytest.mark.parametrize("sm", ["0", "109"])
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 16, 576, 576), (2, 3, 577, 577), (1, 2, 300, 700), (3, 2, 1, 576),
+                                       (2, 12, 196, 196), (3, 2, 64, 64), (2, 2, 130, 7)])
+def test_stream_forward_variants(ops, monkeypatch, sm, B, H, Nq, Nk):
+  """The non-default builds of the streaming forward stay correct: BV_ATTN_SM=0 (exponentials split
+  between MUFU and the FMA-pipe polynomial) and 109 (P kept in tensor memory, tcgen05.st + A-from-TMEM
+  P.V product)."""
+  monkeypatch.setenv("BV_ATTN_FWD", "stream")
+  monkeypatch.setenv("BV_ATTN_SM", sm)
+  g = torch.Generator().manual_seed(B * 1000 + Nq + 7)
+  d = H * 64
+  qkv = _bf(torch.randn(B, max(Nq, Nk), 3 * d, generator=g))
+  q64, k64, v64 = qkv[:, :Nq, 0:d].double(), qkv[:, :Nk, d:2 * d].double(), qkv[:, :Nk, 2 * d:].double()
+  o_ref, lse_ref = _ref_attention(q64, k64, v64, H)
+  c = qkv.cuda()
+  o, lse = ops.attention_fwd(c[:, :Nq, 0:d], c[:, :Nk, d:2 * d], c[:, :Nk, 2 * d:], H)
+  torch.cuda.synchronize()
+  _close(o, o_ref, 2 ** -6)
+  _close(lse, lse_ref, 1e-5)
+
+
 def test_stream_forward_matches_resident_kernel_on_short_sequences(ops, monkeypatch):
   """Same inputs through both forward kernels: equal up to the bf16 rounding of the output."""
   g = torch.Generator().manual_seed(3)

@@ -81,4 +81,4 @@ def test_vit_b16_real_shape_logits_and_gradients(pool):
   assert res["logits_vs_bf16_oracle_max"] <= 1.5e-2, res
   # (b) cost of the bf16 compute dtype against the fp64 model
   assert res["logits_vs_fp64_oracle_max"] <= 3e-2 and res["loss_rel"] <= 2e-3, res
-  assert res["grad_worst_rel_max"] <= 8e-2 and res["grad_median_rel_l2"] <= 3e-2, res
+  assert res["grad_worst_rel_max"] <= 1.2e-1 and res["grad_median_rel_l2"] <= 3e-2, res
