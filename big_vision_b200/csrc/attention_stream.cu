@@ -38,7 +38,7 @@ constexpr int F2_O_OFF = F2_P_OFF + 2 * 2 * TILE_BYTES;       // 16 KB staging o
 constexpr int F2_ST_OFF = F2_O_OFF + TILE_BYTES;              // stats [w][buf][m|l][128] fp32 = 4 KB
 constexpr int F2_BAR_OFF = F2_ST_OFF + 2 * 2 * 2 * 128 * 4;
 constexpr int F2_SMEM = F2_BAR_OFF + 512 + 1024;
-constexpr int F2_DEFAULT_VAR = 9;               // softmax variant (see softmax_block); BV_ATTN_SM overrides
+constexpr int F2_DEFAULT_VAR = 108;              // softmax variant (see softmax_block); BV_ATTN_SM overrides
 
 struct Fwd2Dev {
   int tiles;          // B * H * QT
