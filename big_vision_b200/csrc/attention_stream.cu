@@ -30,14 +30,22 @@ using namespace attn;
 
 constexpr int F2_THREADS = 512;
 constexpr int BK = 128;                         // keys per block
-constexpr int F2_NST = 3;                       // K/V ring stages
-constexpr int F2_Q_OFF = 0;                                   // 2 x 16 KB
-constexpr int F2_KV_OFF = 2 * TILE_BYTES;                     // NST x (K 16 KB + V 16 KB)
-constexpr int F2_P_OFF = F2_KV_OFF + F2_NST * 2 * TILE_BYTES; // 2 x 32 KB
-constexpr int F2_O_OFF = F2_P_OFF + 2 * 2 * TILE_BYTES;       // 16 KB staging of the output tile
-constexpr int F2_ST_OFF = F2_O_OFF + TILE_BYTES;              // stats [w][buf][m|l][128] fp32 = 4 KB
-constexpr int F2_BAR_OFF = F2_ST_OFF + 2 * 2 * 2 * 128 * 4;
-constexpr int F2_SMEM = F2_BAR_OFF + 512 + 1024;
+// Shared memory: Q (2 x 16 KB) | K/V ring (NST x 32 KB) | [P: 2 x 32 KB, only when P goes through shared
+// memory] | output staging 16 KB | stats 4 KB | barriers.  With P in tensor memory (TSP) the 64 KB of
+// the P buffers buy two more ring stages: the ncu source view of the 3-stage build showed the softmax
+// warps waiting on s_full, i.e. on K/V blocks whose slot is only released two blocks ahead of their use
+// (TMA latency ~ one block time).
+template <bool TSP> struct F2L {
+  static constexpr int NST = TSP ? 5 : 3;
+  static constexpr int Q_OFF = 0;
+  static constexpr int KV_OFF = 2 * TILE_BYTES;
+  static constexpr int P_OFF = KV_OFF + NST * 2 * TILE_BYTES;
+  static constexpr int O_OFF = P_OFF + (TSP ? 0 : 2 * 2 * TILE_BYTES);
+  static constexpr int ST_OFF = O_OFF + TILE_BYTES;               // stats [w][buf][m|l][128] fp32 = 4 KB
+  static constexpr int BAR_OFF = ST_OFF + 2 * 2 * 2 * 128 * 4;
+  static constexpr int SMEM = BAR_OFF + 512 + 1024;
+};
+static_assert(F2L<true>::SMEM <= 232448 && F2L<false>::SMEM <= 232448, "shared memory budget");
 constexpr int F2_DEFAULT_VAR = 108;              // softmax variant (see softmax_block); BV_ATTN_SM overrides
 
 struct Fwd2Dev {
@@ -200,21 +208,24 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  using LY = F2L<TSP>;
+  constexpr int F2_NST = LY::NST, F2_Q_OFF = LY::Q_OFF, F2_KV_OFF = LY::KV_OFF, F2_P_OFF = LY::P_OFF,
+                F2_O_OFF = LY::O_OFF, F2_ST_OFF = LY::ST_OFF, F2_BAR_OFF = LY::BAR_OFF;
 
   const uint32_t bar = base + F2_BAR_OFF;
   auto q_full = [&](int s) { return bar + 8u * s; };                    // 0,1
   auto q_empty = [&](int s) { return bar + 8u * (2 + s); };             // 2,3
-  auto kv_full = [&](int s) { return bar + 8u * (4 + s); };             // 4..6
-  auto kv_empty = [&](int s) { return bar + 8u * (7 + s); };            // 7..9
-  auto s_full = [&](int w) { return bar + 8u * (10 + w); };             // 10,11
-  auto s_empty = [&](int w) { return bar + 8u * (12 + w); };            // 12,13
-  auto p_full = [&](int w) { return bar + 8u * (14 + w); };             // 14,15
-  auto p_empty = [&](int w) { return bar + 8u * (16 + w); };            // 16,17
-  auto o_full = [&](int w, int b) { return bar + 8u * (18 + 2 * w + b); };    // 18..21
-  auto o_empty = [&](int w, int b) { return bar + 8u * (22 + 2 * w + b); };   // 22..25
-  auto st_full = [&](int w, int b) { return bar + 8u * (26 + 2 * w + b); };   // 26..29
-  const uint32_t tmem_slot = bar + 8u * 30;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + F2_BAR_OFF + 8 * 30);
+  auto kv_full = [&](int s) { return bar + 8u * (4 + s); };             // 4..8
+  auto kv_empty = [&](int s) { return bar + 8u * (9 + s); };            // 9..13
+  auto s_full = [&](int w) { return bar + 8u * (14 + w); };             // 14,15
+  auto s_empty = [&](int w) { return bar + 8u * (16 + w); };            // 16,17
+  auto p_full = [&](int w) { return bar + 8u * (18 + w); };             // 18,19
+  auto p_empty = [&](int w) { return bar + 8u * (20 + w); };            // 20,21
+  auto o_full = [&](int w, int b) { return bar + 8u * (22 + 2 * w + b); };    // 22..25
+  auto o_empty = [&](int w, int b) { return bar + 8u * (26 + 2 * w + b); };   // 26..29
+  auto st_full = [&](int w, int b) { return bar + 8u * (30 + 2 * w + b); };   // 30..33
+  const uint32_t tmem_slot = bar + 8u * 34;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + F2_BAR_OFF + 8 * 34);
   float* stats = reinterpret_cast<float*>(base_ptr + F2_ST_OFF);   // [(w*2+b)*2 + {0: m, 1: l}][128]
 
   const int warp = threadIdx.x >> 5;
@@ -555,7 +566,7 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   if (warp >= 12) {
     // ---------------- gradient write-out warpgroup ----------------
-    reg_dec<112>();
+    reg_dec<104>();
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int etid = threadIdx.x - 384;
@@ -656,7 +667,7 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     if (etid == 0) tma_store_wait<0>();
   } else if (warp >= 8) {
-    reg_dec<64>();
+    reg_dec<56>();
   }
   if (warp == 8) {
     // ---------------- TMA producer ----------------
@@ -753,7 +764,7 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
   } else if (warp < 8) {
     // ---------------- compute warps ----------------
-    reg_inc<168>();
+    reg_inc<176>();
     const int quarter = warp & 3, hf = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
@@ -764,18 +775,26 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float* __restrict__ p_delta = pin_reg(p.delta);
     const bool mixed_exp = (pin_reg(p.variant) & 4) != 0;
     uint32_t pc = 0;
+    // row statistics (lse in log2 units, delta) are fetched ONE PAIR AHEAD: the ncu source view of the
+    // first build showed 7 % of all stall samples on the use of this load right before the S/dP wait
+    auto load_stats = [&](int gi_, int qt_, float& l2_, float& dl_) {
+      l2_ = INFINITY; dl_ = 0.f;
+      if (gi_ >= my_groups) return;
+      const int bh_ = (static_cast<int>(blockIdx.x) + gi_ * static_cast<int>(gridDim.x)) / pKT;
+      const int qrow_ = qt_ * TQ + row;
+      // padded query rows: lse = +inf makes P exactly 0, their dO rows are TMA zero-fill
+      if (qrow_ < pNq) {
+        l2_ = __ldg(p_lse + static_cast<int64_t>(bh_) * pNq + qrow_);
+        dl_ = __ldg(p_delta + static_cast<int64_t>(bh_) * pNq + qrow_);
+      }
+    };
+    float l2n, dln;
+    load_stats(0, 0, l2n, dln);
     for (int gi = 0; gi < my_groups; ++gi) {
-      const int group = blockIdx.x + gi * gridDim.x;
-      const int bh = group / pKT;
-      const float* lse_i = p_lse + static_cast<int64_t>(bh) * pNq;
-      const float* delta_i = p_delta + static_cast<int64_t>(bh) * pNq;
       for (int qt = 0; qt < QT; ++qt, ++pc) {
         const uint32_t pp = pc & 1u;
-        const int qrow = qt * TQ + row;
-        // row statistics straight from global memory (in flight while the tensor core works on S/dP);
-        // padded query rows: lse = +inf makes P exactly 0, their dO rows are TMA zero-fill
-        float l2 = INFINITY, dl = 0.f;
-        if (qrow < pNq) { l2 = __ldg(lse_i + qrow) * LOG2E; dl = __ldg(delta_i + qrow); }
+        const float l2 = l2n * LOG2E, dl = dln;
+        if (qt + 1 < QT) load_stats(gi, qt + 1, l2n, dln); else load_stats(gi + 1, 0, l2n, dln);
         mbar_wait(sdp_full, pp);
         tc_fence_after();
         float pe[64];
@@ -925,9 +944,9 @@ int launch_attention_fwd_stream(const AttnArgs& a, cudaStream_t s) {
 #define F2_LAUNCH(V, T)                                                                                         \
   case V + (T ? 100 : 0):                                                                                       \
     rc = check_cuda(cudaFuncSetAttribute(attn_fwd_stream_kernel<V, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         F2_SMEM), "cudaFuncSetAttribute(attn_fwd_stream)");                     \
+                                         F2L<T>::SMEM), "cudaFuncSetAttribute(attn_fwd_stream)");                \
     if (rc) return rc;                                                                                          \
-    attn_fwd_stream_kernel<V, T><<<grid, F2_THREADS, F2_SMEM, s>>>(tmQ, tmK, tmV, tmO, p);                      \
+    attn_fwd_stream_kernel<V, T><<<grid, F2_THREADS, F2L<T>::SMEM, s>>>(tmQ, tmK, tmV, tmO, p);                 \
     break;
   switch (var) {
     F2_LAUNCH(0, false) F2_LAUNCH(5, false) F2_LAUNCH(8, false) F2_LAUNCH(9, false) F2_LAUNCH(12, false)
