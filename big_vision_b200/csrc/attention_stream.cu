@@ -32,9 +32,10 @@ constexpr int F2_THREADS = 512;
 constexpr int BK = 128;                         // keys per block
 // Shared memory: Q (2 x 16 KB) | K/V ring (NST x 32 KB) | [P: 2 x 32 KB, only when P goes through shared
 // memory] | output staging 16 KB | stats 4 KB | barriers.  With P in tensor memory (TSP) the 64 KB of
-// the P buffers buy two more ring stages: the ncu source view of the 3-stage build showed the softmax
-// warps waiting on s_full, i.e. on K/V blocks whose slot is only released two blocks ahead of their use
-// (TMA latency ~ one block time).
+// the P buffers buy two more ring stages.  (The ncu source view of the 3-stage build shows 11 % of the
+// stall samples on the softmax warps' s_full wait; the deeper ring changed the 576-key time from 1.433
+// to 1.421 ms, so K/V latency was not what they were waiting for -- the scores of a warpgroup's next
+// block can only be issued once it has started the current one.)
 template <bool TSP> struct F2L {
   static constexpr int NST = TSP ? 5 : 3;
   static constexpr int Q_OFF = 0;
@@ -775,8 +776,9 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float* __restrict__ p_delta = pin_reg(p.delta);
     const bool mixed_exp = (pin_reg(p.variant) & 4) != 0;
     uint32_t pc = 0;
-    // row statistics (lse in log2 units, delta) are fetched ONE PAIR AHEAD: the ncu source view of the
-    // first build showed 7 % of all stall samples on the use of this load right before the S/dP wait
+    // row statistics (lse, delta) are fetched ONE PAIR AHEAD: the ncu source view of the first build
+    // showed 7 % of all stall samples on the use of this load right before the S/dP wait (measured
+    // effect on the kernel time: none outside the noise, the wait simply moved to sdp_full)
     auto load_stats = [&](int gi_, int qt_, float& l2_, float& dl_) {
       l2_ = INFINITY; dl_ = 0.f;
       if (gi_ >= my_groups) return;
