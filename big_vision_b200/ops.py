@@ -334,7 +334,9 @@ def drop_cls(x, n, N0):
 
 def siglip_loss(dots, row_offset, t_param, b_param, global_b, loss, dt, db):
   n, B = dots.shape
-  G = torch.empty((n, B), dtype=torch.bfloat16, device=dots.device)
+  # G feeds two GEMMs through TMA: its row stride must be a multiple of 16 bytes (8 bf16) even when the
+  # slab is narrow (the chunked loss on a tiny per-rank batch: [4, 4])
+  G = torch.empty((n, (B + 7) // 8 * 8), dtype=torch.bfloat16, device=dots.device)[:, :B]
   # per-block partials + fixed-order finishing pass: the scalars are run-to-run deterministic
   ws = torch.empty(L.LOSS_WS_FLOATS, dtype=torch.float32, device=dots.device)
   L.call("bv_siglip_loss", _p(dots), n, B, dots.stride(0), row_offset, _p(t_param), _p(b_param),
@@ -345,7 +347,7 @@ def siglip_loss(dots, row_offset, t_param, b_param, global_b, loss, dt, db):
 def softmax_contrastive_loss(dots, row_offset, t_param, global_b, weight, loss, dt, ncorrect):
   """One direction of the CLIP softmax loss on dots [n, B]; returns G (bf16) = d loss / d dots."""
   n, B = dots.shape
-  G = torch.empty((n, B), dtype=torch.bfloat16, device=dots.device)
+  G = torch.empty((n, (B + 7) // 8 * 8), dtype=torch.bfloat16, device=dots.device)[:, :B]
   ws = torch.empty(3 * n, dtype=torch.float32, device=dots.device)
   L.call("bv_softmax_contrastive_loss", _p(dots), n, B, dots.stride(0), row_offset, _p(t_param), global_b,
          float(weight), _p(G), G.stride(0), _p(loss), _p(dt), _p(ncorrect), _p(ws), _stream())

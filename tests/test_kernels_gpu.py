@@ -255,6 +255,27 @@ def test_siglip_loss_slab(ops, n, B, off):
   _close(db, br.grad, 1e-4)
 
 
+def test_narrow_loss_slab_feeds_the_gradient_gemms(ops):
+  """The chunked loss on a tiny per-rank batch produces [4, 4] slabs (2 ranks x 4 pairs,
+  tests/test_dist_gpu.py): the bf16 gradient slab must still be a legal TMA operand (row stride a
+  multiple of 16 bytes) for G . z and G^T . z."""
+  g = torch.Generator().manual_seed(0)
+  n = 4
+  zi = _bf(torch.randn(n, 64, generator=g) * 0.1)
+  zt = _bf(torch.randn(n, 64, generator=g) * 0.1)
+  dots = ops.gemm(zi.cuda(), zt.cuda(), out_dtype=torch.float32)
+  sc = torch.zeros(3, device="cuda")
+  t, b = torch.tensor([math.log(10.0)]).cuda(), torch.tensor([-10.0]).cuda()
+  G = ops.siglip_loss(dots, 0, t, b, 8, sc[0:1], sc[1:2], sc[2:3])
+  assert G.shape == (n, n) and (G.stride(0) * 2) % 16 == 0
+  dzi = ops.gemm(G, zt.cuda(), b_mn=True, out_dtype=torch.float32)
+  dzt = ops.gemm(G, zi.cuda(), a_mn=True, b_mn=True, out_dtype=torch.float32)
+  _close(dzi, G.double().cpu() @ zt.double(), 1e-4)
+  _close(dzt, G.double().cpu().T @ zi.double(), 1e-4)
+  G2 = ops.softmax_contrastive_loss(dots, 0, t, 8, 0.5, sc[0:1], sc[1:2], sc[2:3])
+  _close(ops.gemm(G2, zt.cuda(), b_mn=True, out_dtype=torch.float32), G2.double().cpu() @ zt.double(), 1e-4)
+
+
 @pytest.mark.parametrize("n,B,off", [(8, 8, 0), (64, 256, 128), (33, 100, 7)])
 def test_softmax_contrastive_slab(ops, n, B, off):
   """One direction of the CLIP softmax loss (_deprecated_contrastive.py:80-101) on a rank's [n, B]
