@@ -71,5 +71,34 @@ def build(force=False, verbose=True):
   return LIB
 
 
+def build_variant(defines, suffix):
+  """An experimental build of the same sources with extra -D flags into libbv_b200_<suffix>.so (own
+  object directory); selected at run time with BV_LIB_PATH.  Not part of build()."""
+  bdir = os.path.join(HERE, "build_" + suffix)
+  os.makedirs(bdir, exist_ok=True)
+  objs = []
+
+  def one(src):
+    obj = os.path.join(bdir, src.replace(".cu", ".o"))
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+      raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return obj
+
+  with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    objs = list(ex.map(one, SOURCES))
+  lib = os.path.join(HERE, f"libbv_b200_{suffix}.so")
+  r = subprocess.run([NVCC, "-shared", "-o", lib] + objs + ["-lcudart"], capture_output=True, text=True)
+  if r.returncode != 0:
+    raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+  print(f"[build] linked {lib}")
+  return lib
+
+
 if __name__ == "__main__":
-  build(force="--force" in sys.argv)
+  if "--variant" in sys.argv:      # python -m big_vision_b200.build --variant BV_MBAR_SUSPEND_NS=20000 hint
+    i = sys.argv.index("--variant")
+    build_variant(sys.argv[i + 1].split(","), sys.argv[i + 2])
+  else:
+    build(force="--force" in sys.argv)

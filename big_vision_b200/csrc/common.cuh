@@ -120,9 +120,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// BV_MBAR_SUSPEND_NS (build-time experiment, `python -m big_vision_b200.build --variant`): pass an
+// explicit suspend-time hint so that a waiting warp is parked by the hardware for up to that long
+// instead of returning to the polling loop after the (shorter, implementation-defined) default.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
+#ifdef BV_MBAR_SUSPEND_NS
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(BV_MBAR_SUSPEND_NS))
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -132,6 +146,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
   } while (!ok);
 }
 // non-blocking: has the phase with this parity completed?
