@@ -438,6 +438,7 @@ struct BwdDev {
   long long ldo, bso, lddo, bsdo;
   float* dq_colsum; float* dk_colsum; float* dv_colsum;   // optional [H*64] bias gradients
   int variant;       // BV_BWD_VARIANT (bring-up experiments; 0 = default)
+  int in_bytes;      // bytes the four operand boxes of one item bring in (boxes are 128 rows when N <= 128)
   long long* dbg;    // optional timeline of CTA 0 (BV_ATTN_DBG=1)
 };
 // dbg[256 + slot] : per-pair events (16 per pair, first 12 pairs) of CTA 0
@@ -653,7 +654,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ph = static_cast<uint32_t>(it) & 1u;
         // operands are free once every MMA of the previous item retired
         mbar_wait(in_empty, ph ^ 1u);
-        mbar_expect_tx(in_full, 4 * OP_BYTES);
+        mbar_expect_tx(in_full, static_cast<uint32_t>(p.in_bytes));
         tma_load_3d(do_s, &tmdO, in_full, h * DH, 0, b);
         tma_load_3d(q_s, &tmQ, in_full, h * DH, 0, b);
         tma_load_3d(k_s, &tmK, in_full, h * DH, 0, b);
@@ -1119,12 +1120,17 @@ int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
   CUtensorMap tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV;
   // BV_ATTN_BWD_PIPE=1: per-tile operand pipeline (bring-up switch, see attn_bwd_kernel<PIPE>)
   const bool pipe = [] { const char* e = getenv("BV_ATTN_BWD_PIPE"); return e && e[0] == '1'; }();
-  const uint32_t in_rows = pipe ? TQ : BWD_ROWS;       // operand boxes: one tile, or the whole item
-  if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, in_rows))) return rc;
-  if ((rc = make_tmap_bnd(&tmK, a.k, cols, a.Nk, a.B, a.ldk, a.bsk, in_rows))) return rc;
-  if ((rc = make_tmap_bnd(&tmV, a.v, cols, a.Nk, a.B, a.ldv, a.bsv, in_rows))) return rc;
-  if ((rc = make_tmap_bnd(&tmO, a.o, cols, a.Nq, a.B, a.ldo, a.bso, in_rows))) return rc;
-  if ((rc = make_tmap_bnd(&tmdO, g.d_o, cols, a.Nq, a.B, g.lddo, g.bsdo, in_rows))) return rc;
+  // operand boxes: one tile (PIPE), or the whole item -- 128 rows are enough for a single-tile operand
+  // (the 64-token text tower, the 1-query MAP head): a 256-row box would spend half of its shared-memory
+  // writes on TMA zero-fill
+  const uint32_t q_rows = pipe ? TQ : (a.Nq <= TQ ? TQ : BWD_ROWS);
+  const uint32_t k_rows = pipe ? TQ : (a.Nk <= TQ ? TQ : BWD_ROWS);
+  p.in_bytes = static_cast<int>(2 * q_rows * 128 + 2 * k_rows * 128);
+  if ((rc = make_tmap_bnd(&tmQ, a.q, cols, a.Nq, a.B, a.ldq, a.bsq, q_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmK, a.k, cols, a.Nk, a.B, a.ldk, a.bsk, k_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmV, a.v, cols, a.Nk, a.B, a.ldv, a.bsv, k_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmO, a.o, cols, a.Nq, a.B, a.ldo, a.bso, q_rows))) return rc;
+  if ((rc = make_tmap_bnd(&tmdO, g.d_o, cols, a.Nq, a.B, g.lddo, g.bsdo, q_rows))) return rc;
   if ((rc = make_tmap_bnd(&tmdQ, g.dq, cols, a.Nq, a.B, g.lddq, g.bsdq, TQ))) return rc;
   if ((rc = make_tmap_bnd(&tmdK, g.dk, cols, a.Nk, a.B, g.lddk, g.bsdk, TQ))) return rc;
   if ((rc = make_tmap_bnd(&tmdV, g.dv, cols, a.Nk, a.B, g.lddv, g.bsdv, TQ))) return rc;
