@@ -13,8 +13,8 @@ run() {  # tag env...
   tail -1 gpurun_out/r02_bench_${N}gpu_$tag.json | cut -c1-260
   grep "step \|nccl" gpurun_out/r02_bench_${N}gpu_$tag.err | head -6
 }
-run overlap BV_X=1
-run single BV_GRAD_ALLREDUCE=single
+run single BV_X=1
+run overlap BV_GRAD_ALLREDUCE=overlap
 timeout -s KILL 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
   --master-port 29812 bench.py --impl torch_gpu --gpus $N --steps 4 --warmup 3 > gpurun_out/r02_bench_${N}gpu_torch.json 2> gpurun_out/r02_bench_${N}gpu_torch.err
 tail -1 gpurun_out/r02_bench_${N}gpu_torch.json | cut -c1-400
