@@ -37,6 +37,7 @@ struct FwdDev {
   float* lse;         // [B, H, Nq]
   long long* dbg;     // optional timeline of CTA 0 (bring-up aid, BV_ATTN_DBG=1), else null
   int sm_var;         // softmax tuning variant (BV_ATTN_SM, bit 0 = independent max / sum chains)
+  int pack;           // 1: every 128-row tile holds TWO 64-token items (block-diagonal scores), see launcher
 };
 
 // dbg[(tile_i * 16 + event)] = clock64() for the first 32 tiles of CTA 0
@@ -72,7 +73,7 @@ struct SoftmaxCtx {
   float* xch;
   float* lse;
   long long* dbg;
-  int my_tiles, NKP, Nk, Nq, QT, nbuf;
+  int my_tiles, NKP, Nk, Nq, QT, nbuf, pack, H;
   float scale_log2;
 };
 
@@ -102,6 +103,11 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
   const float scale_log2 = pin_reg(c.scale_log2);
   float* xch = pin_reg(c.xch);
   const int nbuf = pin_reg(c.nbuf), NKP = pin_reg(c.NKP), QT = pin_reg(c.QT), Nq = pin_reg(c.Nq);
+  // packed tiles (two 64-token items, block-diagonal scores): rows 0..63 own key columns 0..63 (this
+  // thread's half iff hf == 0), rows 64..127 own columns 64..127 (hf == 1); the other half of the row is
+  // masked: probability 0, no contribution to max / sum.  Warp-uniform (a warp is 32 rows of one half).
+  const bool dead = pin_reg(c.pack) != 0 && ((row < 64) != (hf == 0));
+  const int pH = pin_reg(c.H);
 #define UNIT_ON(u) (NU ? ((u) < NU) : ((u) < nunits))
   for (int i = 0; i < c.my_tiles; ++i) {
     const int tile = blockIdx.x + i * gridDim.x;
@@ -127,7 +133,9 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       if (UNIT_ON(u)) {
-        if (u * 8 + 8 <= valid) {
+        if (dead) {
+          // masked half of a packed tile
+        } else if (u * 8 + 8 <= valid) {
           // every column of this unit is a real key (warp-uniform test): no per-element masking
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -160,7 +168,10 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
         float e[8];
         // exp2(scale * s - scale * max); ALL_MUFU (default since round 2: measured faster, the FMA
         // pipe is the co-bottleneck) or units alternating between MUFU and the FMA-pipe polynomial
-        if (!ALL_MUFU && (u & 1)) {
+        if (dead) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = 0.f;
+        } else if (!ALL_MUFU && (u & 1)) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) e[j] = ex2_poly(fmaf(__uint_as_float(sv[u][j]), scale_log2, -mxs));
         } else {
@@ -201,8 +212,13 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
     if (hf == 0) {
       xch[512 + (i & 1) * 128 + row] = 1.0f / sum;
       const int qrow = qt * TQ + row;
-      if (qrow < Nq && c.lse != nullptr)
-        c.lse[static_cast<int64_t>(bh) * Nq + qrow] = (mxs + log2f(sum)) * LN2;
+      if (qrow < Nq && c.lse != nullptr) {
+        // packed: tile bh = (b', h) holds images 2b' (rows 0..63) and 2b'+1 (rows 64..127); lse stays in
+        // the caller's [B, H, 64] layout
+        const int64_t li = c.pack ? (static_cast<int64_t>(bh + (bh / pH) * pH + (row >> 6) * pH) * 64 + (row & 63))
+                                  : (static_cast<int64_t>(bh) * Nq + qrow);
+        c.lse[li] = (mxs + log2f(sum)) * LN2;
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(c.inv_full0 + 8u * (i & 1));
@@ -393,15 +409,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     c.s_full0 = s_full(0); c.s_empty0 = s_empty(0); c.p_full = p_full; c.p_empty = p_empty;
     c.inv_full0 = inv_full(0); c.inv_empty0 = inv_empty(0);
     c.NKP = p.NKP; c.Nk = p.Nk; c.Nq = p.Nq; c.QT = p.QT; c.nbuf = p.nbuf; c.scale_log2 = p.scale_log2;
+    c.pack = p.pack; c.H = p.H;
     c.lse = p.lse; c.dbg = p.dbg;
     const int nunits = p.NKP >> 4;
     if (p.sm_var >> 2 == 2) {
       if (nunits == 13) softmax_warpgroups<13, true>(c);
+      else if (nunits == 8) softmax_warpgroups<8, true>(c);     // 128 keys: two packed 64-token items
       else if (nunits == 4) softmax_warpgroups<4, true>(c);
       else if (nunits == 16) softmax_warpgroups<16, true>(c);
       else softmax_warpgroups<0, true>(c);
     } else {
       if (nunits == 13) softmax_warpgroups<13, false>(c);
+      else if (nunits == 8) softmax_warpgroups<8, false>(c);
       else if (nunits == 4) softmax_warpgroups<4, false>(c);
       else if (nunits == 16) softmax_warpgroups<16, false>(c);
       else softmax_warpgroups<0, false>(c);
@@ -439,6 +458,7 @@ struct BwdDev {
   float* dq_colsum; float* dk_colsum; float* dv_colsum;   // optional [H*64] bias gradients
   int variant;       // BV_BWD_VARIANT (bring-up experiments; 0 = default)
   int in_bytes;      // bytes the four operand boxes of one item bring in (boxes are 128 rows when N <= 128)
+  int pack;          // 1: every item is TWO 64-token (image, head) items in one 128 x 128 pair (block-diagonal)
   long long* dbg;    // optional timeline of CTA 0 (BV_ATTN_DBG=1)
 };
 // dbg[256 + slot] : per-pair events (16 per pair, first 12 pairs) of CTA 0
@@ -865,6 +885,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const long long p_ldo = p.ldo, p_bso = p.bso, p_lddo = p.lddo, p_bsdo = p.bsdo;
     const int wmode = pin_reg(p.variant) & 3;
     const bool mixed_exp = (pin_reg(p.variant) & 4) != 0;
+    const int p_pack = pin_reg(p.pack);
+    // packed items: this thread's 64 key columns belong to the other image -> P = dS = 0 (warp-uniform)
+    const bool dead = p_pack != 0 && ((row < 64) != (hf == 0));
     // ---- prologue of item `pit`: delta = rowsum(O o dO) and lse (log2 units) for its 256 row slots,
     // straight from global memory while the TMA loads are in flight; buffers alternate per item
     auto prologue = [&](int pit) {
@@ -902,7 +925,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           acc += __shfl_xor_sync(0xffffffffu, acc, 4);
           if (chunk == 0) delta_i[(tid >> 3) + 32 * i] = acc;
         }
-        lse2_i[tid] = tid < pNq ? p_lse[static_cast<int64_t>(bh) * pNq + tid] * LOG2E : INFINITY;
+        // packed items: rows 0..63 = image 2b', rows 64..127 = image 2b'+1, lse in the caller's [B,H,64] layout
+        const int64_t li = p_pack ? (static_cast<int64_t>(bh + (bh / pH) * pH + (tid >> 6) * pH) * 64 + (tid & 63))
+                                  : (static_cast<int64_t>(bh) * pNq + tid);
+        lse2_i[tid] = tid < pNq ? p_lse[li] * LOG2E : INFINITY;
       }
     };
     if constexpr (PIPE) {
@@ -943,7 +969,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // dQ product against zero-filled K rows.  Everything stays finite.
             // Exponentials: all on MUFU (BV_BWD_VARIANT bit 2 clear, the default since round 2) or
             // alternating between MUFU and the FMA-pipe polynomial (see ex2_poly).
-            if (!mixed_exp) {
+            if (dead) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) pe[j] = 0.f;
+            } else if (!mixed_exp) {
 #pragma unroll
               for (int j = 0; j < 64; ++j) {
                 const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
@@ -1020,6 +1049,17 @@ int check_attn(const AttnArgs& a, const char* who) {
   return BV_OK;
 }
 
+// Two 64-token items per 128-row tile (see launch_attention_fwd): needs self-attention over exactly 64
+// tokens, an even batch, and every operand's images back to back (batch stride == 64 row strides).
+// BV_ATTN_PACK=0 switches it off (A/B measurements, tests).
+bool can_pack(const AttnArgs& a, const void* extra, int64_t ld_extra, int64_t bs_extra) {
+  const char* e = getenv("BV_ATTN_PACK");
+  if (e && e[0] == '0') return false;
+  if (a.Nq != 64 || a.Nk != 64 || (a.B & 1)) return false;
+  (void)extra;
+  return a.bsq == 64 * a.ldq && a.bsk == 64 * a.ldk && a.bsv == 64 * a.ldv && bs_extra == 64 * ld_extra;
+}
+
 // Which forward kernel: sequences whose scores fit in TMEM (Nk <= 256) can use the whole-key-range
 // kernel of this file; longer ones need the key-block streaming kernel (attention_stream.cu), which
 // also handles the short ones.  BV_ATTN_FWD = "resident" | "stream" forces one for A/B measurements.
@@ -1053,13 +1093,20 @@ int attn_debug_read(long long* host, int n) {
   return n;
 }
 
-int launch_attention_fwd(const AttnArgs& a, cudaStream_t s) {
-  int rc = check_attn(a, "bv_attention_fwd");
+int launch_attention_fwd(const AttnArgs& a_in, cudaStream_t s) {
+  int rc = check_attn(a_in, "bv_attention_fwd");
   if (rc) return rc;
-  if (use_stream_fwd(a)) return launch_attention_fwd_stream(a, s);
+  if (use_stream_fwd(a_in)) return launch_attention_fwd_stream(a_in, s);
   FwdDev p;
   p.dbg = attn_debug_buffer();
   { const char* e = getenv("BV_ATTN_SM"); p.sm_var = e ? atoi(e) : 8; }   // bits 2..: 2 = all exponentials on MUFU
+  // Packing: a 64-token item (the text tower) fills half of a 128-row tile.  When the images lie back
+  // to back in memory (batch stride == 64 rows, true for the fused QKV buffer) two consecutive images
+  // are ONE box of 128 rows: the kernel runs on B/2 items of 128 tokens with block-diagonal scores
+  // (the cross-image quarter tiles are masked to probability 0).  Half the tiles, no padded rows.
+  AttnArgs a = a_in;
+  p.pack = can_pack(a_in, a_in.o, a_in.ldo, a_in.bso) ? 1 : 0;
+  if (p.pack) { a.B = a_in.B / 2; a.Nq = a.Nk = 128; a.bsq *= 2; a.bsk *= 2; a.bsv *= 2; a.bso *= 2; }
   p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
   p.QT = (a.Nq + TQ - 1) / TQ;
   p.NKP = (a.Nk + 15) / 16 * 16;
@@ -1085,19 +1132,35 @@ int launch_attention_fwd(const AttnArgs& a, cudaStream_t s) {
   return check_cuda(cudaGetLastError(), "attn_fwd_kernel launch");
 }
 
-int launch_attention_bwd(const AttnBwdArgs& g, cudaStream_t s) {
-  const AttnArgs& a = g.f;
-  int rc = check_attn(a, "bv_attention_bwd");
+int launch_attention_bwd(const AttnBwdArgs& g_in, cudaStream_t s) {
+  int rc = check_attn(g_in.f, "bv_attention_bwd");
   if (rc) return rc;
-  if (a.lse == nullptr) { set_error("bv_attention_bwd: lse required"); return BV_ERR_INVALID; }
+  if (g_in.f.lse == nullptr) { set_error("bv_attention_bwd: lse required"); return BV_ERR_INVALID; }
   {
     // long sequences stream 128-key tiles (attention_stream.cu); BV_ATTN_BWD=stream forces that kernel
     // for short ones too when its workspaces were passed (A/B measurements, tests)
     const char* e = getenv("BV_ATTN_BWD");
-    const bool force = e && e[0] == 's' && g.dq_accum != nullptr && g.delta != nullptr;
-    if (a.Nq > 256 || a.Nk > 256 || force) return launch_attention_bwd_stream(g, s);
+    const bool force = e && e[0] == 's' && g_in.dq_accum != nullptr && g_in.delta != nullptr;
+    if (g_in.f.Nq > 256 || g_in.f.Nk > 256 || force) return launch_attention_bwd_stream(g_in, s);
   }
   BwdDev p;
+  // two 64-token items per 128 x 128 pair (see launch_attention_fwd); every tensor must have its images
+  // back to back
+  AttnBwdArgs gp = g_in;
+  {
+    const AttnArgs& f = g_in.f;
+    const bool ok = can_pack(f, f.o, f.ldo, f.bso) && g_in.bsdo == 64 * g_in.lddo && g_in.bsdq == 64 * g_in.lddq &&
+                    g_in.bsdk == 64 * g_in.lddk && g_in.bsdv == 64 * g_in.lddv &&
+                    !([] { const char* e = getenv("BV_ATTN_BWD_PIPE"); return e && e[0] == '1'; }());
+    p.pack = ok ? 1 : 0;
+    if (ok) {
+      gp.f.B = f.B / 2; gp.f.Nq = gp.f.Nk = 128;
+      gp.f.bsq *= 2; gp.f.bsk *= 2; gp.f.bsv *= 2; gp.f.bso *= 2;
+      gp.bsdo *= 2; gp.bsdq *= 2; gp.bsdk *= 2; gp.bsdv *= 2;
+    }
+  }
+  const AttnBwdArgs& g = gp;
+  const AttnArgs& a = gp.f;
   p.BH = static_cast<int>(a.B * a.H);
   p.H = a.H; p.Nq = a.Nq; p.Nk = a.Nk;
   p.QT = (a.Nq + TQ - 1) / TQ;

@@ -141,7 +141,8 @@ def _ref_attention(q, k, v, heads):
 
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(3, 2, 64, 64), (2, 12, 196, 196), (5, 3, 197, 197), (4, 2, 1, 196),
-                                       (2, 1, 16, 16), (1, 2, 256, 256), (2, 2, 130, 7)])
+                                       (2, 1, 16, 16), (1, 2, 256, 256), (2, 2, 130, 7),
+                                       (4, 3, 64, 64), (6, 12, 64, 64)])   # even batch of 64 tokens: packed tiles
 def test_attention_forward_backward(ops, B, H, Nq, Nk):
   g = torch.Generator().manual_seed(B * 1000 + Nq)
   d = H * 64
@@ -169,6 +170,26 @@ def test_attention_forward_backward(ops, B, H, Nq, Nk):
   for i, t in enumerate((dq, dk, dv)):
     ref = 1 + t.double().sum((0, 1))
     assert (cs[i].double() - ref).abs().max().item() <= 1e-4 * (ref.abs().max().item() + 1)
+
+
+def test_packed_text_tiles_equal_unpacked(ops, monkeypatch):
+  """Two 64-token items per 128-row tile with block-diagonal scores (the text tower at an even batch):
+  same results as one item per tile, forward and backward, including the fused bias gradients."""
+  g = torch.Generator().manual_seed(11)
+  B, H, N = 8, 12, 64
+  d = H * 64
+  c = _bf(torch.randn(B, N, 3 * d, generator=g)).cuda()
+  do = _bf(torch.randn(B, N, d, generator=g)).cuda()
+  q, k, v = c[:, :, 0:d], c[:, :, d:2 * d], c[:, :, 2 * d:]
+  res = {}
+  for mode in ("0", "1"):
+    monkeypatch.setenv("BV_ATTN_PACK", mode)
+    o, lse = ops.attention_fwd(q, k, v, H)
+    cs = torch.zeros(3, d, device="cuda")
+    dq, dk, dv = ops.attention_bwd(do, q, k, v, o, lse, H, dq_colsum=cs[0], dk_colsum=cs[1], dv_colsum=cs[2])
+    res[mode] = (o, lse, dq, dk, dv, cs)
+  for a, b, tol in zip(res["1"], res["0"], (2 ** -8, 1e-6, 2 ** -7, 2 ** -7, 2 ** -7, 1e-4)):
+    _close(a, b, tol)
 
 
 def test_attention_rows_are_convex_combinations(ops):
