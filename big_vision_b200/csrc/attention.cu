@@ -1,13 +1,16 @@
 // Scaled-dot-product attention forward / backward on tcgen05 (K5, and the MAP
-// head's 1-query attention, K10).  Reference: flax.linen.MultiHeadDotProductAttention
-// as called at models/vit.py:93-98 (self-attention, no mask, no dropout) and
-// models/vit.py:176-178 (MAPHead probe attention): q is scaled by 1/sqrt(dh), softmax
-// over keys, weights times v.  Head dim is fixed at 64 (every ViT variant in
-// models/vit.py:297-300 has width/heads == 64 except "mu").
+// head's 1-query attention, K10) for sequences whose keys fit on chip.  Reference:
+// flax.linen.MultiHeadDotProductAttention as called at models/vit.py:93-98 (self-attention, no
+// mask, no dropout) and models/vit.py:176-178 (MAPHead probe attention): q is scaled by
+// 1/sqrt(dh), softmax over keys, weights times v.  Head dim is fixed at 64 (every ViT variant in
+// models/vit.py:297-300 has width/heads == 64 except "mu" and So400m).
 //
-// All keys of one (image, head) fit on chip (N <= 256 here: 196/197 image tokens,
-// 64 text tokens), so scores for a 128-query tile live in TMEM as a single
-// [128 x Nk] fp32 tile and the softmax is exact (no online rescaling).
+// These are the RESIDENT kernels: all keys of one (image, head) fit on chip (N <= 256: 196/197
+// image tokens, 64 text tokens), so scores for a 128-query tile live in TMEM as a single
+// [128 x Nk] fp32 tile and the softmax is exact (no online rescaling).  Longer sequences (config 5:
+// 576 keys) go to the key-block streaming kernels of attention_stream.cu; the launchers here
+// dispatch.  64-token items (the text tower) are packed two per 128-row tile with block-diagonal
+// scores (can_pack / launch_attention_fwd).
 //
 // q/k/v/o are strided views into the fused QKV GEMM output: element (b, t, h*64+j)
 // at base + b*batch_stride + t*row_stride + h*64 + j; 3-D TMA descriptors read them
