@@ -117,6 +117,13 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
     const int qt = tile % QT;
     const int bh = tile / QT;
     const int bf = i % nbuf;
+    // no real query row in this warp's 32 rows of the tile (the second tile of a 196-token item holds
+    // 68 rows): nothing to exponentiate; the rows it would produce are clipped by the output store
+#ifdef BV_NO_DEAD_SKIP      // A/B build (python -m big_vision_b200.build --variant BV_NO_DEAD_SKIP noskip)
+    const bool dead_t = dead;
+#else
+    const bool dead_t = dead || (qt * TQ + quarter * 32 >= Nq);
+#endif
     mbar_wait(c.s_full0 + 8u * bf, static_cast<uint32_t>(i / nbuf) & 1u);
     tc_fence_after();
     SM_DBG(3, i);
@@ -136,8 +143,8 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
       if (UNIT_ON(u)) {
-        if (dead) {
-          // masked half of a packed tile
+        if (dead_t) {
+          // masked half of a packed tile, or rows past Nq
         } else if (u * 8 + 8 <= valid) {
           // every column of this unit is a real key (warp-uniform test): no per-element masking
 #pragma unroll
@@ -171,7 +178,7 @@ __device__ __forceinline__ void softmax_warpgroups(const SoftmaxCtx c) {
         float e[8];
         // exp2(scale * s - scale * max); ALL_MUFU (default since round 2: measured faster, the FMA
         // pipe is the co-bottleneck) or units alternating between MUFU and the FMA-pipe polynomial
-        if (dead) {
+        if (dead_t) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) e[j] = 0.f;
         } else if (!ALL_MUFU && (u & 1)) {
@@ -972,9 +979,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // dQ product against zero-filled K rows.  Everything stays finite.
             // Exponentials: all on MUFU (BV_BWD_VARIANT bit 2 clear, the default since round 2) or
             // alternating between MUFU and the FMA-pipe polynomial (see ex2_poly).
-            if (dead) {
+            // live key columns of this thread's 64-column half in this key tile, and whether the warp's
+            // 32 query rows hold any real query: P = dS = 0 elsewhere costs nothing to produce (the
+            // 196-token items leave 68 rows / columns in their second tile)
+#ifdef BV_NO_DEAD_SKIP
+            const int ncl = 64;
+            const bool dead_p = dead;
+#else
+            int ncl = pNk - kt * TQ - hf * 64;
+            ncl = ncl > 64 ? 64 : ncl;
+            const bool dead_p = dead || ncl <= 0 || (qt * TQ + quarter * 32 >= pNq);
+#endif
+            if (dead_p) {
 #pragma unroll
               for (int j = 0; j < 64; ++j) pe[j] = 0.f;
+            } else if (ncl < 64) {
+#pragma unroll
+              for (int u8 = 0; u8 < 8; ++u8) {
+                if (u8 * 8 < ncl) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const int j = u8 * 8 + jj;
+                    const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
+                    pe[j] = ex2_mufu(fmaf(sj, p_scale_log2, -l2));
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) pe[u8 * 8 + jj] = 0.f;
+                }
+              }
             } else if (!mixed_exp) {
 #pragma unroll
               for (int j = 0; j < 64; ++j) {

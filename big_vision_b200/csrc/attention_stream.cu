@@ -792,7 +792,9 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     };
     float l2n, dln;
     load_stats(0, 0, l2n, dln);
+    const int pNk = pin_reg(p.Nk);
     for (int gi = 0; gi < my_groups; ++gi) {
+      const int kt_cur = (static_cast<int>(blockIdx.x) + gi * static_cast<int>(gridDim.x)) % pKT;
       for (int qt = 0; qt < QT; ++qt, ++pc) {
         const uint32_t pp = pc & 1u;
         const float l2 = l2n * LOG2E, dl = dln;
@@ -807,7 +809,34 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tmem_ld_wait();
           // no key masking needed: padded key columns only feed dV/dK rows that the TMA store clips
           // and a dQ product against zero-filled K rows; everything stays finite
-          if (!mixed_exp) {
+          // live key columns of this thread's half in this key tile / any real query row in this warp:
+          // P = dS = 0 elsewhere (576 tokens leave 64 rows / columns in the fifth tile)
+#ifdef BV_NO_DEAD_SKIP
+          const int ncl = 64;
+          if (false) {
+#else
+          int ncl = pNk - kt_cur * TQ - hf * 64;
+          ncl = ncl > 64 ? 64 : ncl;
+          if (ncl <= 0 || (qt * TQ + quarter * 32 >= pNq)) {
+#endif
+#pragma unroll
+            for (int j = 0; j < 64; ++j) pe[j] = 0.f;
+          } else if (ncl < 64) {
+#pragma unroll
+            for (int u8 = 0; u8 < 8; ++u8) {
+              if (u8 * 8 < ncl) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const int j = u8 * 8 + jj;
+                  const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
+                  pe[j] = ex2_mufu(fmaf(sj, p_scale_log2, -l2));
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) pe[u8 * 8 + jj] = 0.f;
+              }
+            }
+          } else if (!mixed_exp) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
               const float sj = __uint_as_float(j < 32 ? t0[j & 31] : t1[j & 31]);
