@@ -1,19 +1,23 @@
 #!/bin/bash
-# Final check of the round: the driver's own commands (pytest -x -m gpu, smoke, default bench) + config 5.
+# Final check of the round with the driver's own commands: pytest -x -m gpu, smoke, default bench, reference arm;
+# plus the other BASELINE workloads (short) so that every bench line exists on the final tree.
 mkdir -p gpurun_out
 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/r02_pytest_gpu_final.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py --steps 8 --warmup 3 --profile-calls > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err
 grep "step \|attention\|(all)\|layernorm" gpurun_out/r02_bench_final.err | head -7
-timeout -s KILL 600 python bench.py --impl reference --steps 2 --warmup 1 | cut -c1-300
-timeout -s KILL 900 python bench.py --workload siglip_l14_336 --steps 3 --warmup 3 --no-cpu-baseline --no-gpu-baseline --profile-calls \
-  > gpurun_out/r02_bench_l14_final.json 2> gpurun_out/r02_bench_l14_final.err
-grep "step \|attention\|(all)\|layernorm" gpurun_out/r02_bench_l14_final.err | head -7
+for w in vit_b16_cls mixer_b16 vit_s16 siglip_l14_336; do
+  st=10; [ $w = siglip_l14_336 ] && st=3
+  timeout -s KILL 600 python bench.py --workload $w --steps $st --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/r02_bench_final_$w.json 2>/dev/null
+done
 python - <<'PY'
 import json
-for f in ["r02_bench_final", "r02_bench_l14_final"]:
-  d = json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
+for f in ["r02_bench_final", "r02_bench_final_vit_b16_cls", "r02_bench_final_mixer_b16", "r02_bench_final_vit_s16", "r02_bench_final_siglip_l14_336"]:
+  try:
+    d = json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
+  except Exception as e:
+    print(f, "ERR", e); continue
   g, c = d.get("gpu_baseline") or {}, d.get("cpu_baseline") or {}
   print(f, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "torch_gpu", g.get("value"), "cpu", c.get("value"),
-        "frac", round(d["roofline"]["frac"], 3), "mfu", round(d["roofline"]["step_mfu"], 3), "launches", d["gpu_launches"], d["clocks"])
+        "frac", round(d["roofline"]["frac"], 3), "mfu", round(d["roofline"]["step_mfu"], 3), "launches", d["gpu_launches"], d["clocks"]["sm_mhz"])
 PY
