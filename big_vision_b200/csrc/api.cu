@@ -118,6 +118,10 @@ int bv_pool_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int64_t n,
                 int32_t d, int32_t mode, int32_t tok, void* stream) {
   return launch_pool_bwd(dy, dy_dtype, dx, dx_dtype, n, N, d, mode, tok, S(stream));
 }
+int bv_pool_max_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype,
+                    int64_t n, int32_t N, int32_t d, void* stream) {
+  return launch_pool_max_bwd(dy, dy_dtype, x, x_dtype, dx, dx_dtype, n, N, d, S(stream));
+}
 int bv_broadcast_row(const void* x, int x_dtype, const float* row, void* y, int y_dtype,
                      int64_t rows, int32_t d, void* stream) {
   return launch_add_rows(x, x_dtype, row, y, y_dtype, rows, d, S(stream));

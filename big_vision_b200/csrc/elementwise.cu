@@ -302,8 +302,8 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dz, const float* __r
 }
 
 // ---------------------------------------------------------------------------
-// pooling over tokens: mode 0 = mean (gap), mode 1 = select token `tok`
-// (models/vit.py:245-253, text_transformer.py:82-88)
+// pooling over tokens: mode 0 = mean (gap), mode 1 = select token `tok`, mode 2 = max (gmp)
+// (models/vit.py:245-253, text_transformer.py:82-90)
 // ---------------------------------------------------------------------------
 __global__ void pool_fwd_kernel(const void* __restrict__ x, int xdt, void* __restrict__ y, int ydt,
                                 int64_t n, int N, int d, int mode, int tok) {
@@ -317,10 +317,35 @@ __global__ void pool_fwd_kernel(const void* __restrict__ x, int xdt, void* __res
       float s = 0.f;
       for (int t = 0; t < N; ++t) s += ld_as_float(x, xdt, (b * N + t) * d + c);
       r = s / static_cast<float>(N);
+    } else if (mode == 2) {
+      r = ld_as_float(x, xdt, b * N * d + c);
+      for (int t = 1; t < N; ++t) r = fmaxf(r, ld_as_float(x, xdt, (b * N + t) * d + c));
     } else {
       r = ld_as_float(x, xdt, (b * N + tok) * d + c);
     }
     st_from_float(y, ydt, idx, r);
+  }
+}
+// d max / d x: the cotangent goes to the positions that hold the maximum, split evenly between
+// ties (the rule jnp.max differentiates with); one thread per (item, channel) column
+__global__ void pool_max_bwd_kernel(const void* __restrict__ dy, int ydt, const void* __restrict__ x,
+                                    int xdt, void* __restrict__ dx, int dxdt, int64_t n, int N, int d) {
+  const int64_t total = n * d;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % d);
+    const int64_t b = idx / d;
+    float m = ld_as_float(x, xdt, b * N * d + c);
+    int ties = 1;
+    for (int t = 1; t < N; ++t) {
+      const float v = ld_as_float(x, xdt, (b * N + t) * d + c);
+      if (v > m) { m = v; ties = 1; } else if (v == m) { ++ties; }
+    }
+    const float g = ld_as_float(dy, ydt, idx) / static_cast<float>(ties);
+    for (int t = 0; t < N; ++t) {
+      const int64_t at = (b * N + t) * d + c;
+      st_from_float(dx, dxdt, at, ld_as_float(x, xdt, at) == m ? g : 0.f);
+    }
   }
 }
 __global__ void pool_bwd_kernel(const void* __restrict__ dy, int ydt, void* __restrict__ dx,
@@ -543,15 +568,23 @@ int launch_l2norm_bwd(const float* dz, const float* z, const float* norm, void* 
 
 int launch_pool(const void* x, int xdt, void* y, int ydt, int64_t n, int N, int d, int mode,
                 int tok, cudaStream_t s) {
-  if (mode != 0 && (tok < 0 || tok >= N)) { set_error("bv_pool: token index out of range"); return BV_ERR_INVALID; }
+  if (mode < 0 || mode > 2) { set_error("bv_pool: mode must be 0 (mean), 1 (token) or 2 (max)"); return BV_ERR_INVALID; }
+  if (mode == 1 && (tok < 0 || tok >= N)) { set_error("bv_pool: token index out of range"); return BV_ERR_INVALID; }
   pool_fwd_kernel<<<grid_for(n * d, 256, 148 * 16), 256, 0, s>>>(x, xdt, y, ydt, n, N, d, mode, tok);
   return check_launch("pool_fwd_kernel");
 }
 int launch_pool_bwd(const void* dy, int ydt, void* dx, int xdt, int64_t n, int N, int d, int mode,
                     int tok, cudaStream_t s) {
+  if (mode == 2) { set_error("bv_pool_bwd: the max pool needs its input, use bv_pool_max_bwd"); return BV_ERR_INVALID; }
   if (mode != 0 && (tok < 0 || tok >= N)) { set_error("bv_pool_bwd: token index out of range"); return BV_ERR_INVALID; }
   pool_bwd_kernel<<<grid_for(n * N * d, 256, 148 * 16), 256, 0, s>>>(dy, ydt, dx, xdt, n, N, d, mode, tok);
   return check_launch("pool_bwd_kernel");
+}
+int launch_pool_max_bwd(const void* dy, int ydt, const void* x, int xdt, void* dx, int dxdt, int64_t n,
+                        int N, int d, cudaStream_t s) {
+  if (n <= 0 || N <= 0 || d <= 0) { set_error("bv_pool_max_bwd: empty problem"); return BV_ERR_INVALID; }
+  pool_max_bwd_kernel<<<grid_for(n * d, 256, 148 * 16), 256, 0, s>>>(dy, ydt, x, xdt, dx, dxdt, n, N, d);
+  return check_launch("pool_max_bwd_kernel");
 }
 
 int launch_add_rows(const void* x, int xdt, const float* row, void* y, int ydt, int64_t rows,

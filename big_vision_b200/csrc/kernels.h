@@ -87,6 +87,8 @@ int launch_pool(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, int
                 int mode, int tok_offset, cudaStream_t s);
 int launch_pool_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int64_t n, int N, int d,
                     int mode, int tok_offset, cudaStream_t s);
+int launch_pool_max_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx,
+                        int dx_dtype, int64_t n, int N, int d, cudaStream_t s);
 int launch_add_rows(const void* x, int x_dtype, const float* row, void* y, int y_dtype,
                     int64_t rows, int d, cudaStream_t s);
 int launch_tanh_fwd(const void* x, void* y, int dtype, int64_t n, cudaStream_t s);

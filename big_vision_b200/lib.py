@@ -78,6 +78,7 @@ SIGNATURES = {
     "bv_l2norm_bwd": [c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_f32, c_vp],
     "bv_pool_fwd": [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp],
     "bv_pool_bwd": [c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "bv_pool_max_bwd": [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp],
     "bv_broadcast_row": [c_vp, c_i32, c_vp, c_vp, c_i32, c_i64, c_i32, c_vp],
     "bv_tanh_fwd": [c_vp, c_vp, c_i32, c_i64, c_vp],
     "bv_tanh_bwd": [c_vp, c_vp, c_vp, c_i32, c_i64, c_vp],

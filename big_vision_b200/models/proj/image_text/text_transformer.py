@@ -2,7 +2,8 @@
 big_vision/models/proj/image_text/text_transformer.py:29-99.
 
 Embed(vocab, width) + learned posemb -> vit.Encoder (no attention mask: none is passed at
-text_transformer.py:72-75) -> pool ("last" by default, :82-84) -> Dense head (:97-98).
+text_transformer.py:72-75) -> pool ("last" by default; "first", "mean"/"gap", "max"/"gmp", "map",
+:82-93) -> Dense head (:97-98).
 `out["vocab_logits"]` (:80) is dead in training and is never computed here.
 
 The reference runs this tower in fp32 (it has no dtype_mm field); BASELINE.json's configs
@@ -37,9 +38,11 @@ class _Model:
   def __post_init__(self):
     if self.dropout:
       raise NotImplementedError("dropout > 0 is not on the benchmarked path")
-    if self.pool_type not in ("last", "first", "mean", "gap"):
-      raise NotImplementedError(f"Cannot do pooling '{self.pool_type}' on this path yet")
+    if self.pool_type not in ("last", "first", "mean", "gap", "max", "gmp", "map"):
+      raise NotImplementedError(f"Cannot do pooling '{self.pool_type}'")
     self.prefix = (self.name + "/") if self.name else ""
+    self.map_head = (vit.MAPHead(self.prefix + "MAPHead_0/", self.width, self.mlp_dim, self.num_heads)
+                     if self.pool_type == "map" else None)
     self.encoder = vit.Encoder(self.prefix + "Encoder_0/", self.depth, self.width,
                                self.mlp_dim, self.num_heads, scan=self.scan, remat_policy=self.remat_policy)
     self._len = None
@@ -54,6 +57,10 @@ class _Model:
     ]
     s, aliases = self.encoder.specs()
     specs += s
+    if self.map_head is not None:
+      s, a = self.map_head.specs()
+      specs += s
+      aliases += a
     if self.num_classes:
       specs += [E.ParamSpec(p + "head/kernel", (d, self.num_classes), E.lecun_normal(d)),
                 E.ParamSpec(p + "head/bias", (self.num_classes,), E.zeros)]
@@ -83,7 +90,14 @@ class _Model:
     else:
       encd, mean, rstd = ops.layernorm_fwd(x, P.f(en + "scale"), P.f(en + "bias"))
       saved["norm"] = (x, mean, rstd)
-      out = ops.pool_fwd(encd, n, Ln, 0)
+      if self.map_head is not None:
+        out, saved["map"] = self.map_head.fwd(P, encd, n, Ln)
+        out = vit._Model._to16(out)
+      elif self.pool_type in ("max", "gmp"):
+        out = ops.pool_fwd(encd, n, Ln, 2)
+        saved["encd"] = encd
+      else:
+        out = ops.pool_fwd(encd, n, Ln, 0)
     if self.num_classes:
       saved["head_in"] = out
       out = ops.gemm(out, P.h(p + "head/kernel"), b_mn=True, bias=P.f(p + "head/bias"),
@@ -109,7 +123,13 @@ class _Model:
                               dbias=P.g(en + "bias"), dx_colsum=last_b)
       dx = ops.pool_bwd(dxt, n, Ln, 1, tok=tok)
     else:
-      denc = ops.pool_bwd(dout, n, Ln, 0)
+      if self.map_head is not None:
+        denc = self.map_head.bwd(P, ops.cast(dout, torch.empty_like(dout, dtype=torch.float32)),
+                                 saved["map"], n, Ln)
+      elif self.pool_type in ("max", "gmp"):
+        denc = ops.pool_max_bwd(dout, saved["encd"], n, Ln)
+      else:
+        denc = ops.pool_bwd(dout, n, Ln, 0)
       dx = ops.layernorm_bwd(denc, xs, P.f(en + "scale"), mean, rstd, dscale=P.g(en + "scale"),
                              dbias=P.g(en + "bias"), dx_colsum=last_b)
     dx = self.encoder.bwd(P, dx, saved["enc"], n, Ln, None)

@@ -497,6 +497,10 @@ class _Model:
       x0 = ops.pool_fwd(x, n, N, 1, tok=0)
       out, mean, rstd = ops.layernorm_fwd(x0, P.f(en + "scale"), P.f(en + "bias"), out_dtype=torch.float32)
       saved["norm"] = (x0, mean, rstd)
+    elif self.pool_type == "none":
+      # no pooling (models/vit.py:252-253): pre_logits / head run on every token, out is [n, N, .]
+      out, mean, rstd = ops.layernorm_fwd(x, P.f(en + "scale"), P.f(en + "bias"))
+      saved["norm"] = (x, mean, rstd)
     else:
       raise ValueError(f"Unknown pool type: '{self.pool_type}'")
     if self.rep_size:
@@ -509,6 +513,10 @@ class _Model:
       saved["head_in"] = out
       out = ops.gemm(self._to16(out), P.h(p + "head/kernel"), b_mn=True, bias=P.f(p + "head/bias"),
                      out_dtype=torch.float32)
+    if self.pool_type == "none":
+      if out.dtype != torch.float32:
+        out = ops.cast(out, torch.empty_like(out, dtype=torch.float32))
+      out = out.view(n, N, -1)
     return out, saved
 
   @staticmethod
@@ -518,10 +526,12 @@ class _Model:
     return ops.cast(x, torch.empty_like(x, dtype=torch.bfloat16))
 
   def bwd(self, P, dout, saved):
-    """dout: fp32 [n, out].  Accumulates parameter gradients into P.grad."""
+    """dout: fp32 [n, out] ([n, N, out] without pooling).  Accumulates parameter gradients into P.grad."""
     p, d = self.prefix, self.width
     n, N = saved["n"], saved["N"]
     en = self.prefix + "Transformer/encoder_norm/"
+    if self.pool_type == "none":
+      dout = dout.reshape(n * N, -1)
     if self.num_classes:
       d16 = self._to16(dout)
       ops.colsum(dout, P.g(p + "head/bias"))
@@ -539,8 +549,8 @@ class _Model:
       x, mean, rstd = saved["norm"]
       dx = ops.layernorm_bwd(denc, x, P.f(en + "scale"), mean, rstd, dscale=P.g(en + "scale"),
                              dbias=P.g(en + "bias"), dx_colsum=last_b)
-    elif self.pool_type == "gap":
-      denc = ops.pool_bwd(dout, n, N, 0)
+    elif self.pool_type in ("gap", "none"):
+      denc = ops.pool_bwd(dout, n, N, 0) if self.pool_type == "gap" else self._to16(dout)
       x, mean, rstd = saved["norm"]
       dx = ops.layernorm_bwd(denc, x, P.f(en + "scale"), mean, rstd, dscale=P.g(en + "scale"),
                              dbias=P.g(en + "bias"), dx_colsum=last_b)

@@ -254,6 +254,13 @@ def pool_bwd(dy, n, N, mode, tok=0, dx_dtype=torch.bfloat16):
   return dx
 
 
+def pool_max_bwd(dy, x, n, N, dx_dtype=torch.bfloat16):
+  d = dy.shape[-1]
+  dx = torch.empty((n * N, d), dtype=dx_dtype, device=dy.device)
+  L.call("bv_pool_max_bwd", _p(dy), _dt(dy), _p(x), _dt(x), _p(dx), _dt(dx), n, N, d, _stream())
+  return dx
+
+
 def broadcast_row(x, rows, row=None, out_dtype=None):
   d = x.shape[-1]
   y = torch.empty((rows, d), dtype=out_dtype or x.dtype, device=x.device)

@@ -157,11 +157,16 @@ int bv_l2norm_fwd(const void* x, int x_dtype, float* z, float* norm, int64_t n, 
                   float eps, void* stream);
 int bv_l2norm_bwd(const float* dz, const float* z, const float* norm, void* dx, int dx_dtype,
                   int64_t n, int32_t d, float eps, void* stream);
-/* mode 0: mean over tokens (gap); mode 1: take token `tok` (models/vit.py:245-253) */
+/* mode 0: mean over tokens (gap); mode 1: take token `tok` (models/vit.py:245-253);
+   mode 2: max over tokens ("max"/"gmp", text_transformer.py:89-90), backward = bv_pool_max_bwd */
 int bv_pool_fwd(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, int32_t N, int32_t d,
                 int32_t mode, int32_t tok, void* stream);
 int bv_pool_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int64_t n, int32_t N,
                 int32_t d, int32_t mode, int32_t tok, void* stream);
+/* gradient of the mode-2 pool: dy[n,d] goes to the positions of x[n,N,d] holding the column maximum,
+   split evenly between ties (the jnp.max differentiation rule) */
+int bv_pool_max_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype,
+                    int64_t n, int32_t N, int32_t d, void* stream);
 /* y[r,:] = x[0,:] (+ row[:]) for r < rows : broadcast one row (MAP probe, models/vit.py:174) */
 int bv_broadcast_row(const void* x, int x_dtype, const float* row, void* y, int y_dtype,
                      int64_t rows, int32_t d, void* stream);

@@ -177,6 +177,8 @@ def vit_forward(p, image, cfg, mm="float32"):
     x = rnd(x, mm).mean(1)
   elif cfg["pool_type"] in ("0", "tok"):
     x = x[:, 0]
+  elif cfg["pool_type"] == "none":            # models/vit.py:252-253: head applied to every token
+    x = rnd(x, mm)
   else:
     raise ValueError(cfg["pool_type"])
   if cfg.get("rep_size"):
@@ -198,6 +200,10 @@ def text_forward(p, text, cfg, mm="float32"):
     x = x[:, 0, :]
   elif pool in ("mean", "gap"):
     x = rnd(x, mm).mean(1)
+  elif pool in ("max", "gmp"):                # text_transformer.py:89-90; amax splits the cotangent
+    x = torch.amax(rnd(x, mm), dim=1)         # evenly between ties, as jnp.max does
+  elif pool == "map":                         # text_transformer.py:91-93
+    x = map_head(x, sub(p, "MAPHead_0/"), cfg["num_heads"], mm)
   else:
     raise NotImplementedError(pool)
   if cfg.get("num_classes"):

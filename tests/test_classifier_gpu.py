@@ -22,14 +22,15 @@ def _randomize_zero_inits(tree, seed):
   return out
 
 
-def _check(model, oracle_fwd, image_shape, loss_name, num_classes, seed=0, **fwd_kw):
+def _check(model, oracle_fwd, image_shape, loss_name, num_classes, seed=0, tokens=None, **fwd_kw):
   from big_vision_b200 import train
   P = model.init(seed, image_shape, device="cuda")
   tree = _randomize_zero_inits(P.numpy_tree("f"), seed + 1)
   P.load_tree(tree)
   rng = np.random.default_rng(seed + 2)
   image = rng.uniform(-1, 1, size=image_shape).astype(np.float32)
-  labels = np.eye(num_classes, dtype=np.float32)[rng.integers(0, num_classes, size=image_shape[0])]
+  lshape = image_shape[0] if tokens is None else (image_shape[0], tokens)     # per-token labels without pooling
+  labels = np.eye(num_classes, dtype=np.float32)[rng.integers(0, num_classes, size=lshape)]
   loss, logits = train.loss_and_grads(model, P, torch.from_numpy(image).cuda(),
                                       torch.from_numpy(labels).cuda(), loss_name, **fwd_kw)
   # oracle
@@ -56,14 +57,16 @@ def _check(model, oracle_fwd, image_shape, loss_name, num_classes, seed=0, **fwd
 
 @pytest.mark.parametrize("pool,posemb,rep,loss", [("tok", "learn", True, "sigmoid_xent"),
                                                   ("gap", "sincos2d", True, "softmax_xent"),
-                                                  ("0", "learn", False, "sigmoid_xent")])
+                                                  ("0", "learn", False, "sigmoid_xent"),
+                                                  ("none", "learn", True, "softmax_xent")])
 def test_vit_classifier_step(pool, posemb, rep, loss):
   from big_vision_b200.models import vit
   kw = dict(width=64, depth=2, mlp_dim=128, num_heads=1, patch_size=(16, 16), pool_type=pool,
             posemb=posemb, rep_size=rep)
   model = vit.Model(16, **kw)
   cfg = dict(depth=2, num_heads=1, pool_type=pool, posemb=posemb, rep_size=rep, num_classes=16)
-  _check(model, lambda p, img, mm: O.vit_forward(p, img, cfg, mm), (4, 64, 48, 3), loss, 16)
+  _check(model, lambda p, img, mm: O.vit_forward(p, img, cfg, mm), (4, 64, 48, 3), loss, 16,
+         tokens=12 if pool == "none" else None)
 
 
 def test_mlp_mixer_step():

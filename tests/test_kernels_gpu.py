@@ -232,6 +232,16 @@ def test_patchify_embed_pool_l2norm(ops):
   xs = torch.randn(40, 64, generator=g)
   assert torch.allclose(ops.pool_fwd(xs.cuda(), 4, 10, 0).cpu(), xs.reshape(4, 10, 64).mean(1), atol=1e-6)
   assert torch.equal(ops.pool_fwd(xs.cuda(), 4, 10, 1, tok=9).cpu(), xs.reshape(4, 10, 64)[:, 9])
+  # max pool (text_transformer.py:89-90): bf16 input with many ties at the maximum -- the cotangent is
+  # split evenly between them, the rule jnp.max (and torch.amax) differentiates with
+  xm = (torch.randn(6, 9, 64, generator=g) * 2).round().bfloat16()
+  assert torch.equal(ops.pool_fwd(xm.view(54, 64).cuda(), 6, 9, 2).cpu(), xm.amax(1))
+  xr = xm.double().requires_grad_(True)
+  dym = torch.randn(6, 64, generator=g)
+  torch.amax(xr, dim=1).backward(dym.double())
+  assert int((xr.grad != 0).sum()) > 6 * 64          # the case does have ties
+  _close(ops.pool_max_bwd(dym.cuda(), xm.view(54, 64).cuda(), 6, 9, dx_dtype=torch.float32).view(6, 9, 64),
+         xr.grad, 1e-6)
 
 
 @pytest.mark.parametrize("vr,inr,clip", [((-1.0, 1.0), (0.0, 255.0), False), ((-0.5, 0.5), (-256.0, 255.0), True),

@@ -92,6 +92,38 @@ def test_softmax_clip_loss_and_gradients_match_oracle(tiny):
   assert float(np.abs(grads["b"]).max()) == 0.0          # the softmax loss has no bias term
 
 
+@pytest.mark.parametrize("pool", ["first", "mean", "max", "map"])
+def test_text_tower_pooling_variants(pool):
+  """text_transformer.py:82-93: every pooling the reference's text tower offers, through the whole
+  two-tower loss against autograd through the fp64 oracle ("last" is the golden-vector case above)."""
+  from big_vision_b200.models.proj.image_text import two_towers
+  from big_vision_b200.trainers.proj.image_text import siglip
+  kw = dict(common.TINY, text=dict(common.TINY["text"], pool_type=pool))
+  model = two_towers.Model(**kw)
+  P = model.init(3, common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, device="cuda")
+  tree = P.numpy_tree("f")
+  image, text = common.synthetic_batch(common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, 64, seed=4)
+  loss, aux = siglip.loss_and_grads(model, P, torch.from_numpy(image).cuda(), torch.from_numpy(text).cuda())
+  p64 = O.to_f64_tree(tree, requires_grad=True)
+  zi, zt, ex = O.two_towers_forward(p64, torch.from_numpy(image), torch.from_numpy(text), common.oracle_cfg(kw),
+                                    "float32")
+  ref = O.siglip_loss(zi, zt, ex["t"], ex["b"])
+  ref = ref[0] if isinstance(ref, tuple) else ref
+  ref.backward()
+  assert float(loss) == pytest.approx(float(ref), rel=5e-3)
+  grads = P.numpy_tree("g")
+  assert any(k.startswith("txt/MAPHead_0/") for k in grads) == (pool == "map")
+  gmax = max(float(v.grad.abs().max()) for v in p64.values() if v.grad is not None)
+  bad = {}
+  for k, g in grads.items():
+    r = p64[k].grad.numpy() if p64[k].grad is not None else np.zeros_like(g)
+    err = float(np.abs(g.astype(np.float64) - r).max())
+    tol = 6e-2 * float(np.abs(r).max()) + 3e-3 * gmax
+    if err > tol:
+      bad[k] = (err, tol)
+  assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]
+
+
 def test_loss_gradient_is_consistent_with_finite_difference(tiny):
   """d loss / d t' and d loss / d b from the kernels vs a central difference of the kernel loss."""
   from big_vision_b200.trainers.proj.image_text import siglip

@@ -183,3 +183,30 @@ def test_mixer_stochastic_depth_schedule_and_masks():
   assert tuple(masks.shape) == (12, 2, 4096) and set(np.unique(masks.numpy())) <= {0.0, 1.0}
   assert float(masks[0].min()) == 1.0
   assert abs(float(1 - masks[11].mean()) - 0.1) < 0.02
+
+
+def test_text_pooling_variants_and_unpooled_vit():
+  """text_transformer.py:82-95 / models/vit.py:242-255: every pooling of the reference exists in the
+  oracle and in the model's parameter tree; the max pool splits its cotangent between ties (the
+  jnp.max rule), which is what bv_pool_max_bwd implements."""
+  import common
+  from big_vision_b200.models import vit
+  from big_vision_b200.models.proj.image_text import text_transformer
+  x = torch.tensor([[[1.0, 5.0], [3.0, 5.0], [3.0, 2.0]]], dtype=torch.float64, requires_grad=True)
+  torch.amax(x, dim=1).sum().backward()
+  assert x.grad.tolist() == [[[0.0, 0.5], [0.5, 0.5], [0.5, 0.0]]]
+  for pool, extra in [("last", 0), ("first", 0), ("gap", 0), ("gmp", 0), ("map", 15)]:
+    m = text_transformer.Model(32, **dict(common.TINY["text"], pool_type=pool))
+    P = m.init(0, common.TINY_TEXT_SHAPE, device="cpu")
+    names = set(P.tree("f"))
+    assert sum(k.startswith("MAPHead_0/") for k in names) == extra, pool
+    text = torch.from_numpy(common.synthetic_batch(common.TINY_IMAGE_SHAPE, common.TINY_TEXT_SHAPE, 64)[1])
+    z = O.text_forward(O.to_f64_tree(P.numpy_tree("f")), text, dict(depth=2, num_heads=1, pool_type=pool,
+                                                                    num_classes=32))
+    assert tuple(z.shape) == (8, 32)
+  with pytest.raises(NotImplementedError):
+    text_transformer.Model(32, **dict(common.TINY["text"], pool_type="median"))
+  v = vit.Model(16, width=64, depth=1, mlp_dim=128, num_heads=1, patch_size=(16, 16), pool_type="none")
+  P = v.init(0, (2, 32, 48, 3), device="cpu")
+  cfg = dict(depth=1, num_heads=1, pool_type="none", num_classes=16)
+  assert tuple(O.vit_forward(O.to_f64_tree(P.numpy_tree("f")), torch.zeros(2, 32, 48, 3), cfg).shape) == (2, 6, 16)
