@@ -380,19 +380,36 @@ __global__ void add_rows_kernel(const void* __restrict__ x, int xdt, const float
 }
 
 // bf16 [n, N, d] -> [n, d, Np] (Np >= N, pad zero) : Mixer token-mixing transpose
-__global__ void transpose_tokens_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N,
-                                        int d, int Np) {
-  __shared__ bf16 tile[32][33];
+//
+// 64 x 64 tiles, 16-byte global accesses on both sides (eight lanes per 128-byte row).  The tile is
+// written to shared memory already transposed, two bytes at a time, and read back as 16-byte rows;
+// the 8-element column group of row r is XOR-ed with (r / 8) % 8, which spreads the eight row groups a
+// warp writes over distinct banks (an unpadded or 16-byte-padded pitch would put them all on one).
+constexpr int TT = 64;
+__device__ __forceinline__ int tt_swz(int row, int col) { return col ^ (((row >> 3) & 7) << 3); }
+
+__global__ void __launch_bounds__(256)
+transpose_tokens_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int d, int Np) {
+  __shared__ __align__(16) bf16 tile[TT][TT];          // [channel][token], swizzled
   const int64_t b = blockIdx.z;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int t = t0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (t < N && c < d) ? x[(b * N + t) * d + c] : __float2bfloat16(0.f);
+  const int t0 = blockIdx.x * TT, c0 = blockIdx.y * TT;
+  const int sub = threadIdx.x & 7, row = threadIdx.x >> 3;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int tl = pass * 32 + row, t = t0 + tl, c = c0 + sub * 8;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (t < N && c < d) q = *reinterpret_cast<const uint4*>(x + (b * N + t) * d + c);
+    const bf16* e = reinterpret_cast<const bf16*>(&q);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[sub * 8 + i][tt_swz(sub * 8 + i, tl)] = e[i];
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, t = t0 + threadIdx.x;
-    if (c < d && t < Np) y[(b * d + c) * Np + t] = tile[threadIdx.x][i];
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int cl = pass * 32 + row, c = c0 + cl, t = t0 + sub * 8;
+    if (c < d && t < Np)
+      *reinterpret_cast<uint4*>(y + (b * d + c) * Np + t) =
+          *reinterpret_cast<const uint4*>(&tile[cl][tt_swz(cl, sub * 8)]);
   }
 }
 
@@ -456,22 +473,37 @@ __global__ void row_select_kernel(const bf16* __restrict__ a, const bf16* __rest
 
 // out[b,t,c] = (res ? res[b,t,c] : 0) + y[b,c,t]   with y stored [n, d, Np]: inverse of
 // transpose_tokens fused with the residual add (models/mlp_mixer.py:51-52)
-__global__ void untranspose_add_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
-                                       bf16* __restrict__ out, int N, int d, int Np) {
-  __shared__ bf16 tile[32][33];
+__global__ void __launch_bounds__(256)
+untranspose_add_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res,
+                       bf16* __restrict__ out, int N, int d, int Np) {
+  __shared__ __align__(16) bf16 tile[TT][TT];          // [token][channel], swizzled
   const int64_t b = blockIdx.z;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, t = t0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < d && t < N) ? y[(b * d + c) * Np + t] : __float2bfloat16(0.f);
+  const int t0 = blockIdx.x * TT, c0 = blockIdx.y * TT;
+  const int sub = threadIdx.x & 7, row = threadIdx.x >> 3;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int cl = pass * 32 + row, c = c0 + cl, t = t0 + sub * 8;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (c < d && t < Np) q = *reinterpret_cast<const uint4*>(y + (b * d + c) * Np + t);
+    const bf16* e = reinterpret_cast<const bf16*>(&q);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tile[sub * 8 + i][tt_swz(sub * 8 + i, cl)] = e[i];
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int t = t0 + i, c = c0 + threadIdx.x;
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int tl = pass * 32 + row, t = t0 + tl, c = c0 + sub * 8;
     if (t < N && c < d) {
-      float v = __bfloat162float(tile[threadIdx.x][i]);
-      if (res != nullptr) v += __bfloat162float(res[(b * N + t) * d + c]);
-      out[(b * N + t) * d + c] = __float2bfloat16_rn(v);
+      uint4 q = *reinterpret_cast<const uint4*>(&tile[tl][tt_swz(tl, sub * 8)]);
+      if (res != nullptr) {
+        const uint4 r = *reinterpret_cast<const uint4*>(res + (b * N + t) * d + c);
+        bf16* a = reinterpret_cast<bf16*>(&q);
+        const bf16* rr = reinterpret_cast<const bf16*>(&r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          a[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(rr[i]));
+      }
+      *reinterpret_cast<uint4*>(out + (b * N + t) * d + c) = q;
     }
   }
 }
@@ -612,17 +644,19 @@ int launch_axpby(const void* x, const void* y, void* out, int dt, float a, float
   return check_launch("axpby");
 }
 int launch_transpose_tokens(const void* x, void* y, int64_t n, int N, int d, cudaStream_t s) {
+  if (n <= 0 || N <= 0 || d <= 0 || d % 8) { set_error("bv_transpose_tokens: need n,N,d > 0, d %% 8 == 0"); return BV_ERR_INVALID; }
   const int Np = (N + 7) / 8 * 8;
-  dim3 grid((Np + 31) / 32, (d + 31) / 32, static_cast<unsigned>(n));
-  transpose_tokens_kernel<<<grid, dim3(32, 8), 0, s>>>(reinterpret_cast<const bf16*>(x),
+  dim3 grid((Np + TT - 1) / TT, (d + TT - 1) / TT, static_cast<unsigned>(n));
+  transpose_tokens_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x),
                                                       reinterpret_cast<bf16*>(y), N, d, Np);
   return check_launch("transpose_tokens_kernel");
 }
 int launch_untranspose_add(const void* y, const void* res, void* out, int64_t n, int N, int d,
                            cudaStream_t s) {
+  if (n <= 0 || N <= 0 || d <= 0 || d % 8) { set_error("bv_untranspose_add: need n,N,d > 0, d %% 8 == 0"); return BV_ERR_INVALID; }
   const int Np = (N + 7) / 8 * 8;
-  dim3 grid((N + 31) / 32, (d + 31) / 32, static_cast<unsigned>(n));
-  untranspose_add_kernel<<<grid, dim3(32, 8), 0, s>>>(reinterpret_cast<const bf16*>(y),
+  dim3 grid((N + TT - 1) / TT, (d + TT - 1) / TT, static_cast<unsigned>(n));
+  untranspose_add_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(y),
                                                      reinterpret_cast<const bf16*>(res),
                                                      reinterpret_cast<bf16*>(out), N, d, Np);
   return check_launch("untranspose_add_kernel");

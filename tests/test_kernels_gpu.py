@@ -364,3 +364,22 @@ def test_adam_matches_optax_chain(ops, mu_dtype):
       mr = torch.tensor(mr).float().bfloat16().double().numpy()
   _close(p, torch.tensor(pr), 1e-5)
   assert torch.equal(p16.cpu(), p.cpu().bfloat16())
+
+
+@pytest.mark.parametrize("n,N,d", [(3, 196, 768), (2, 12, 64), (2, 197, 72), (1, 64, 128), (2, 130, 200)])
+def test_token_transposes_are_exact(ops, n, N, d):
+  """MLP-Mixer token mixing (models/mlp_mixer.py:49-52): [n, N, d] -> [n, d, Np] with zero padding, and
+  back fused with the residual add.  Pure data movement (+ one rounded add): bit-exact."""
+  g = torch.Generator().manual_seed(n * 1000 + N)
+  x = torch.randn(n, N, d, generator=g).bfloat16()
+  Np = (N + 7) // 8 * 8
+  yt = ops.transpose_tokens(x.view(n * N, d).cuda(), n, N, d).cpu().view(n, d, Np)
+  assert torch.equal(yt[:, :, :N], x.transpose(1, 2))
+  assert float(yt[:, :, N:].abs().max()) == 0.0 if Np > N else True
+  # garbage in the padded columns of the input must not leak into the output
+  y = torch.randn(n, d, Np, generator=g).bfloat16()
+  res = torch.randn(n, N, d, generator=g).bfloat16()
+  back = ops.untranspose_add(y.view(n * d, Np).cuda(), None, n, N, d).cpu().view(n, N, d)
+  assert torch.equal(back, y[:, :, :N].transpose(1, 2))
+  fused = ops.untranspose_add(y.view(n * d, Np).cuda(), res.view(n * N, d).cuda(), n, N, d).cpu().view(n, N, d)
+  assert torch.equal(fused, (y[:, :, :N].transpose(1, 2).float() + res.float()).bfloat16())
