@@ -8,7 +8,8 @@ python bench.py --steps 8 --warmup 3 --profile-calls > gpurun_out/r02_bench_fina
 grep "step \|attention\|(all)\|layernorm" gpurun_out/r02_bench_final.err | head -7
 for w in vit_b16_cls mixer_b16 vit_s16 siglip_l14_336; do
   st=10; [ $w = siglip_l14_336 ] && st=3
-  timeout -s KILL 600 python bench.py --workload $w --steps $st --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/r02_bench_final_$w.json 2>/dev/null
+  timeout -s KILL 600 python bench.py --workload $w --steps $st --warmup 3 --no-cpu-baseline --no-gpu-baseline --profile-calls > gpurun_out/r02_bench_final_$w.json 2> gpurun_out/r02_bench_final_$w.err
+  grep "profile-calls" gpurun_out/r02_bench_final_$w.err | head -12
 done
 python - <<'PY'
 import json
