@@ -179,8 +179,10 @@ class MlpMixer:
       dot = ops.transpose_tokens(dbr, n, N, d)                                # [n*d, Np], pad = 0
       ops.colsum(dot, P.g(b1))
       ops.gemm(hact, dot, a_mn=True, b_mn=True, out=P.g(k1), reduce_out=True, N=N)
-      # [n*d, T]; the Dense_0 bias gradient (column sums) comes out of the same GEMM's epilogue
-      dhpre = ops.gemm(dot, P.h(k1), aux=hpre, epilogue=L.EPI_DGELU, K=N, colsum=P.g(tm + "Dense_0/bias"))
+      dhpre = ops.gemm(dot, P.h(k1), aux=hpre, epilogue=L.EPI_DGELU, K=N)    # [n*d, T]
+      # separate column-sum pass: with n*d rows over only T columns the GEMM epilogue's fused bias
+      # gradient is all atomic contention (measured 2.62 vs 1.26 + 0.07 ms per call)
+      ops.colsum(dhpre, P.g(tm + "Dense_0/bias"))
       ops.gemm(yt, dhpre, a_mn=True, b_mn=True, out=P.g(tm + "Dense_0/kernel"), reduce_out=True, M=N)
       dyt = torch.empty((n * d, Np), dtype=torch.bfloat16, device=dx.device)
       ops.gemm(dhpre, P.h(tm + "Dense_0/kernel"), out=dyt, N=N)
