@@ -68,6 +68,8 @@ for _ in range(2):
   ops.l2norm_bwd(z, z, nrm)
   pl = ops.pool_fwd(x, n, N, 0, out_dtype=torch.float32)
   ops.pool_bwd(pl, n, N, 0)
+  pm = ops.pool_fwd(x, n, N, 2)
+  ops.pool_max_bwd(pm, x, n, N)
   ops.mixup(img, 0.7)
   ops.row_select(x, y, (torch.rand(n, device=dev) > 0.1).float(), n, N)
   yt = ops.transpose_tokens(x, n, N, d)

@@ -22,3 +22,13 @@ for f in ["r02_bench_final", "r02_bench_final_vit_b16_cls", "r02_bench_final_mix
   print(f, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "torch_gpu", g.get("value"), "cpu", c.get("value"),
         "frac", round(d["roofline"]["frac"], 3), "mfu", round(d["roofline"]["step_mfu"], 3), "launches", d["gpu_launches"], d["clocks"]["sm_mhz"])
 PY
+# ncu --set full of the kernels written after the round's main capture (profiles/r02/ncu): the vectorised
+# Mixer transposes and the max pool; digested on the box, text only comes back
+mkdir -p gpurun_out/ncu2 /tmp/ncu2
+timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+  -k regex:'transpose_tokens_kernel|untranspose_add_kernel|pool_max_bwd_kernel|pool_fwd_kernel' \
+  -o /tmp/ncu2/late -f python tools/kernel_zoo.py > gpurun_out/ncu2/late.log 2>&1
+ncu -i /tmp/ncu2/late.ncu-rep --page raw --csv > /tmp/ncu2/late_raw.csv 2>/dev/null
+python tools/ncu_digest.py /tmp/ncu2/late_raw.csv > gpurun_out/ncu2/ncu_summary_late_kernels.md
+gzip -c /tmp/ncu2/late_raw.csv > gpurun_out/ncu2/late_raw.csv.gz
+tail -12 gpurun_out/ncu2/ncu_summary_late_kernels.md
