@@ -14,7 +14,19 @@ vectors for this path.  What pins this file instead:
     keys, DenseGeneral kernel shapes) and are cross-checked in tests/test_oracle.py against
     torch.nn.functional's independent implementations of the same operators;
   * the global loss (siglip.py:287-306) is checked against the explicit per-device form
-    (_deprecated_contrastive.py:117-141) -- two restatements of one quantity must agree.
+    (_deprecated_contrastive.py:117-141) -- two restatements of one quantity must agree;
+  * WHOLE-MODEL pin against code this file shares nothing with (tests/test_oracle_hf_pin.py): the
+    `transformers` package in the image carries SiglipModel -- whose conversion script validates it
+    against the reference's released SigLIP checkpoints -- and ViTForImageClassification, the PyTorch
+    port of the original ViT.  One random parameter tree mapped into both gives, in float64, the same
+    image / text embeddings (1e-7, the difference being the reference's +1e-8 in the normalisation),
+    logits, loss and parameter gradients (1e-6 relative) for the two-tower model with MAP head and
+    last-token text pooling, and the same logits (1e-9), softmax / sigmoid cross-entropies and gradients
+    (1e-8) for the cls-token classifier.  This is not the reference itself, so the "unpinned" label
+    stays; it does pin every flax default listed above plus the [d, h, dh] head split, the MAP head,
+    the class-token / position-embedding order and both losses against an implementation that
+    reproduces the reference's checkpoints.  Not covered by it: MLP-Mixer, sincos2d, gap / "0" pooling,
+    the tanh pre_logits layer (torch cross-checks and source citations only).
 
 `mm="bfloat16"` emulates the CUDA path's rounding points (bf16 matmul operands / outputs and
 a bf16 residual stream, fp32-or-better everywhere else) with straight-through gradients, so
