@@ -210,3 +210,58 @@ def test_text_pooling_variants_and_unpooled_vit():
   P = v.init(0, (2, 32, 48, 3), device="cpu")
   cfg = dict(depth=1, num_heads=1, pool_type="none", num_classes=16)
   assert tuple(O.vit_forward(O.to_f64_tree(P.numpy_tree("f")), torch.zeros(2, 32, 48, 3), cfg).shape) == (2, 6, 16)
+
+
+def test_mixer_oracle_agrees_with_the_module_style_restatement():
+  """No third-party MLP-Mixer is in the image, so unlike the ViT / SigLIP rows (test_oracle_hf_pin.py) the
+  Mixer oracle is only checked against a second, separately written restatement: the nn.Module model of
+  baseline/torch_gpu.py (the labelled GPU stand-in), float64 on CPU.  Two restatements of
+  models/mlp_mixer.py:30-84 that disagreed anywhere (token/channel transposes, LayerNorm placement, the
+  [tokens, tokens_mlp] kernels, mean pooling after pre_head_layer_norm) would show up here."""
+  import importlib.util
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location("torch_gpu_standin", os.path.join(root, "baseline", "torch_gpu.py"))
+  T = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(T)
+  from big_vision_b200.models import mlp_mixer
+  d, blocks, tok, ch, classes = 64, 2, 32, 128, 10
+  T.MIXER["tiny"] = (d, blocks, tok, ch)
+  m = mlp_mixer.Model(classes, patch_size=(16, 16), num_blocks=blocks, hidden_dim=d, tokens_mlp_dim=tok,
+                      channels_mlp_dim=ch)
+  P = m.init(0, (3, 64, 64, 3), device="cpu")
+  rng = np.random.default_rng(5)
+  tree = {k: (v if np.any(v) else (rng.standard_normal(v.shape) * 0.1).astype(np.float32))
+          for k, v in P.numpy_tree("f").items()}
+  t = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in tree.items()}
+  ref = T.Mixer("tiny/16", 64, classes).double().eval()
+  sd = {"stem.weight": t["stem/kernel"].permute(3, 2, 0, 1), "stem.bias": t["stem/bias"],
+        "norm.weight": t["pre_head_layer_norm/scale"], "norm.bias": t["pre_head_layer_norm/bias"],
+        "head.weight": t["head/kernel"].T, "head.bias": t["head/bias"]}
+  for i in range(blocks):
+    b = f"MixerBlock_{i}/"
+    for ln, src in (("ln1", "LayerNorm_0"), ("ln2", "LayerNorm_1")):
+      sd[f"blocks.{i}.{ln}.weight"], sd[f"blocks.{i}.{ln}.bias"] = t[b + src + "/scale"], t[b + src + "/bias"]
+    for mlp, src in (("tok", "token_mixing"), ("ch", "channel_mixing")):
+      for fc, dn in (("fc1", "Dense_0"), ("fc2", "Dense_1")):
+        sd[f"blocks.{i}.{mlp}.{fc}.weight"] = t[f"{b}{src}/{dn}/kernel"].T
+        sd[f"blocks.{i}.{mlp}.{fc}.bias"] = t[f"{b}{src}/{dn}/bias"]
+  assert set(sd) == set(ref.state_dict())
+  ref.load_state_dict({k: v.contiguous() for k, v in sd.items()})
+  image = torch.from_numpy(rng.uniform(-1, 1, size=(3, 64, 64, 3))).double()
+  p64 = O.to_f64_tree(tree, requires_grad=True)
+  mine = O.mixer_forward(p64, image, dict(num_blocks=blocks, num_classes=classes))
+  theirs = ref(image)
+  assert float((mine - theirs).abs().max()) < 1e-10 * max(1.0, float(theirs.abs().max()))
+  labels = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, classes, size=3)), classes).double()
+  O.sigmoid_xent(mine, labels).backward()
+  (-(labels * torch.nn.functional.logsigmoid(theirs) + (1 - labels) * torch.nn.functional.logsigmoid(-theirs))
+   .sum(-1).mean()).backward()
+  g = dict(ref.named_parameters())
+  for name, r in [("stem/kernel", g["stem.weight"].grad.permute(2, 3, 1, 0)),
+                  ("MixerBlock_0/token_mixing/Dense_0/kernel", g["blocks.0.tok.fc1.weight"].grad.T),
+                  ("MixerBlock_1/token_mixing/Dense_1/bias", g["blocks.1.tok.fc2.bias"].grad),
+                  ("MixerBlock_1/channel_mixing/Dense_1/kernel", g["blocks.1.ch.fc2.weight"].grad.T),
+                  ("MixerBlock_0/LayerNorm_1/scale", g["blocks.0.ln2.weight"].grad)]:
+    # (the token-mixing Dense_1 bias shifts all channels of a token alike and every later consumer is a
+    # LayerNorm over channels: its exact gradient is zero, hence the absolute floor)
+    assert float((p64[name].grad - r).abs().max()) <= 1e-9 * float(r.abs().max()) + 1e-14, name
