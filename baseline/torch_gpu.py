@@ -7,7 +7,9 @@ gradient all-reduce, clip + Adam + decoupled weight decay) written in plain PyTo
 cuBLAS GEMMs, `scaled_dot_product_attention` (flash / cuDNN SDPA), fused Adam, DDP's bucketed
 all-reduce -- i.e. the library-kernel implementation a practitioner would run on this box.  It is NOT
 the reference and none of this repository's kernels, models or engine are on its path; `bench.py
---impl torch_gpu` times it on the same synthetic batch as the product arm.
+--impl torch_gpu` times it on the same synthetic batch as the product arm.  That it computes the same
+function is tested on CPU in float64 against the oracle (tests/test_oracle.py:
+test_gpu_standin_computes_the_oracles_siglip_function, test_mixer_oracle_agrees_with_the_module_style_restatement).
 
 Architectures restate big_vision/models/vit.py:57-281, models/proj/image_text/text_transformer.py:29-99,
 models/proj/image_text/two_towers.py:28-90, models/mlp_mixer.py:30-124 and the loss of

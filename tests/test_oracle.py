@@ -212,17 +212,22 @@ def test_text_pooling_variants_and_unpooled_vit():
   assert tuple(O.vit_forward(O.to_f64_tree(P.numpy_tree("f")), torch.zeros(2, 32, 48, 3), cfg).shape) == (2, 6, 16)
 
 
+def _standin():
+  import importlib.util
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec = importlib.util.spec_from_file_location("torch_gpu_standin", os.path.join(root, "baseline", "torch_gpu.py"))
+  T = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(T)
+  return T
+
+
 def test_mixer_oracle_agrees_with_the_module_style_restatement():
   """No third-party MLP-Mixer is in the image, so unlike the ViT / SigLIP rows (test_oracle_hf_pin.py) the
   Mixer oracle is only checked against a second, separately written restatement: the nn.Module model of
   baseline/torch_gpu.py (the labelled GPU stand-in), float64 on CPU.  Two restatements of
   models/mlp_mixer.py:30-84 that disagreed anywhere (token/channel transposes, LayerNorm placement, the
   [tokens, tokens_mlp] kernels, mean pooling after pre_head_layer_norm) would show up here."""
-  import importlib.util
-  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-  spec = importlib.util.spec_from_file_location("torch_gpu_standin", os.path.join(root, "baseline", "torch_gpu.py"))
-  T = importlib.util.module_from_spec(spec)
-  spec.loader.exec_module(T)
+  T = _standin()
   from big_vision_b200.models import mlp_mixer
   d, blocks, tok, ch, classes = 64, 2, 32, 128, 10
   T.MIXER["tiny"] = (d, blocks, tok, ch)
@@ -257,6 +262,7 @@ def test_mixer_oracle_agrees_with_the_module_style_restatement():
   (-(labels * torch.nn.functional.logsigmoid(theirs) + (1 - labels) * torch.nn.functional.logsigmoid(-theirs))
    .sum(-1).mean()).backward()
   g = dict(ref.named_parameters())
+  TOL = 1e-9
   for name, r in [("stem/kernel", g["stem.weight"].grad.permute(2, 3, 1, 0)),
                   ("MixerBlock_0/token_mixing/Dense_0/kernel", g["blocks.0.tok.fc1.weight"].grad.T),
                   ("MixerBlock_1/token_mixing/Dense_1/bias", g["blocks.1.tok.fc2.bias"].grad),
@@ -264,4 +270,92 @@ def test_mixer_oracle_agrees_with_the_module_style_restatement():
                   ("MixerBlock_0/LayerNorm_1/scale", g["blocks.0.ln2.weight"].grad)]:
     # (the token-mixing Dense_1 bias shifts all channels of a token alike and every later consumer is a
     # LayerNorm over channels: its exact gradient is zero, hence the absolute floor)
-    assert float((p64[name].grad - r).abs().max()) <= 1e-9 * float(r.abs().max()) + 1e-14, name
+    assert float((p64[name].grad - r).abs().max()) <= TOL * float(r.abs().max()) + 1e-14, name
+
+
+def test_gpu_standin_computes_the_oracles_siglip_function():
+  """bench.py times baseline/torch_gpu.py beside the product as the labelled stand-in for the reference's
+  GPU build.  That comparison only means something if the stand-in computes the same model and loss: mapped
+  parameters, float64, CPU -- embeddings, loss and gradients must equal the oracle's (which
+  test_oracle_hf_pin.py ties to transformers' SigLIP)."""
+  T = _standin()
+  from big_vision_b200.models.proj.image_text import two_towers
+  d, depth, mlp, heads = 128, 2, 256, 2
+  T.VIT["tiny"] = (d, depth, mlp, heads)
+  tower = dict(width=d, depth=depth, mlp_dim=mlp, num_heads=heads)
+  model = two_towers.Model(image=dict(tower, patch_size=(16, 16), pool_type="map"),
+                           text=dict(tower, vocab_size=32_000), out_dim=(None, d), temperature_init=10.0,
+                           bias_init=-10.0)
+  P = model.init(0, (4, 64, 64, 3), (4, 64), device="cpu")
+  rng = np.random.default_rng(9)
+  tree = {k: (v if np.any(v) else (rng.standard_normal(v.shape) * 0.1).astype(np.float32))
+          for k, v in P.numpy_tree("f").items()}
+  t = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in tree.items()}
+  ref = T.TwoTowers("tiny/16", "tiny", 64, d).double().eval()
+  sd = {"t": t["t"], "b": t["b"]}
+
+  def lin(dst, kernel, bias):
+    sd[dst + ".weight"], sd[dst + ".bias"] = kernel.T, bias
+
+  def norm(dst, src):
+    sd[dst + ".weight"], sd[dst + ".bias"] = t[src + "/scale"], t[src + "/bias"]
+
+  def proj(att, names):                       # reference [d, h, dh] kernels -> one fused [d, k*d] kernel
+    return (torch.cat([t[f"{att}/{n}/kernel"].reshape(d, d) for n in names], 1),
+            torch.cat([t[f"{att}/{n}/bias"].reshape(d) for n in names]))
+
+  def mlp_block(dst, src):
+    lin(dst + ".fc1", t[src + "/Dense_0/kernel"], t[src + "/Dense_0/bias"])
+    lin(dst + ".fc2", t[src + "/Dense_1/kernel"], t[src + "/Dense_1/bias"])
+
+  def encoder(dst, src):
+    for i in range(depth):
+      b, o = f"{src}/encoderblock_{i}", f"{dst}.blocks.{i}"
+      att = b + "/MultiHeadDotProductAttention_0"
+      lin(o + ".attn.qkv", *proj(att, ("query", "key", "value")))
+      lin(o + ".attn.out", t[att + "/out/kernel"].reshape(d, d), t[att + "/out/bias"])
+      norm(o + ".ln1", b + "/LayerNorm_0")
+      norm(o + ".ln2", b + "/LayerNorm_1")
+      mlp_block(o + ".mlp", b + "/MlpBlock_0")
+    norm(dst + ".norm", src + "/encoder_norm")
+
+  sd["img.embed.weight"], sd["img.embed.bias"] = t["img/embedding/kernel"].permute(3, 2, 0, 1), t["img/embedding/bias"]
+  sd["img.pos"] = t["img/pos_embedding"]
+  encoder("img.encoder", "img/Transformer")
+  m = "img/MAPHead_0"
+  sd["img.probe"] = t[m + "/probe"]
+  att = m + "/MultiHeadDotProductAttention_0"
+  lin("img.map_attn.q", *proj(att, ("query",)))
+  lin("img.map_attn.kv", *proj(att, ("key", "value")))
+  lin("img.map_attn.out", t[att + "/out/kernel"].reshape(d, d), t[att + "/out/bias"])
+  norm("img.map_ln", m + "/LayerNorm_0")
+  mlp_block("img.map_mlp", m + "/MlpBlock_0")
+  sd["txt.embed.weight"], sd["txt.pos"] = t["txt/Embed_0/embedding"], t["txt/pos_embedding"]
+  encoder("txt.encoder", "txt/Encoder_0")
+  lin("txt.head", t["txt/head/kernel"], t["txt/head/bias"])
+  assert set(sd) == set(ref.state_dict()), set(sd) ^ set(ref.state_dict())
+  ref.load_state_dict({k: v.contiguous() for k, v in sd.items()})
+  image = torch.from_numpy(rng.uniform(-1, 1, size=(4, 64, 64, 3))).double()
+  text = torch.from_numpy(rng.integers(0, 32_000, size=(4, 64))).int()
+  p64 = O.to_f64_tree(tree, requires_grad=True)
+  cfg = {"image": dict(depth=depth, num_heads=heads, pool_type="map", posemb="learn", rep_size=False, num_classes=None),
+         "text": dict(depth=depth, num_heads=heads, pool_type="last", num_classes=d)}
+  zi, zt, ex = O.two_towers_forward(p64, image, text, cfg, "float32")
+  zi2, zt2 = ref(image, text)
+  # the stand-in hands its embeddings to the loss as float32 (`.float()` after the autocast region), so the
+  # agreement is float32 rounding, not float64
+  assert float((zi - zi2).abs().max()) < 2e-7 and float((zt - zt2).abs().max()) < 2e-7
+  mine = O.siglip_loss(zi, zt, ex["t"], ex["b"])
+  theirs = T.siglip_loss(zi2, zt2, ref.t, ref.b, 0, 4)
+  assert float(mine) == pytest.approx(float(theirs), rel=1e-6)
+  mine.backward()
+  theirs.backward()
+  g = dict(ref.named_parameters())
+  TOL = 1e-5
+  for name, r in [("img/pos_embedding", g["img.pos"].grad), ("img/MAPHead_0/probe", g["img.probe"].grad),
+                  ("txt/head/kernel", g["txt.head.weight"].grad.T), ("t", g["t"].grad), ("b", g["b"].grad),
+                  ("img/Transformer/encoderblock_0/MultiHeadDotProductAttention_0/value/kernel",
+                   g["img.encoder.blocks.0.attn.qkv.weight"].grad.T[:, 2 * d:].reshape(d, heads, d // heads)),
+                  ("img/MAPHead_0/MultiHeadDotProductAttention_0/key/kernel",
+                   g["img.map_attn.kv.weight"].grad.T[:, :d].reshape(d, heads, d // heads))]:
+    assert float((p64[name].grad - r).abs().max()) <= TOL * float(r.abs().max()) + 1e-14, name
