@@ -72,10 +72,10 @@ WORKLOADS = {
              "full update_fn"),
 }
 # ncu-measured DRAM traffic per GEMM launch (all GEMM launches of one siglip_b16 bench run)
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 0.927e9
-NCU_GEMM_DRAM_SOURCE = ("profiles/r01_final_launch_summary.md (ncu dram__bytes_read.sum + dram__bytes_write.sum at 1024 "
-                        "pairs); round-2 cross-check at 256 pairs: 0.216 GB measured vs 0.233 GB algorithmic per launch, "
-                        "profiles/r02/ncu/launch_summary_siglip_b16_n256.md")
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 0.929e9
+NCU_GEMM_DRAM_SOURCE = ("profiles/r02/ncu/launch_summary_siglip_b16_n1024.md (ncu dram__bytes_read.sum + "
+                        "dram__bytes_write.sum over the 1244 GEMM launches of this workload on the final round-2 "
+                        "tree: 1156.1 GB); round 1 measured 0.927 GB (profiles/r01_final_launch_summary.md)")
 
 
 def measured_peaks():
