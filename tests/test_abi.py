@@ -76,3 +76,28 @@ def test_bench_workloads_cover_the_five_baseline_configs():
   assert bench.WORKLOADS["siglip_l14_336"]["per_gpu_batch"] * 8 == 16384 and wl["per_gpu_batch"] * 8 == 8192
   model = bench.build_model(bench.WORKLOADS["siglip_l14_336"])
   assert model.img.scan and model.txt.scan and model.img.width == 1024 and model.img.patch_size == (14, 14)
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+  """The boundary is a C ABI: include/bv_b200.h must compile as C99 (and C++), and a C program that includes
+  it links against libbv_b200.so and can call the entry points that need no GPU."""
+  import shutil
+  import subprocess
+  if shutil.which("gcc") is None:
+    pytest.skip("no gcc")
+  L.load()
+  hdr = os.path.join(ROOT, "include", "bv_b200.h")
+  subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+  subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr], check=True)
+  src = tmp_path / "main.c"
+  src.write_text('#include <stdio.h>\n#include "bv_b200.h"\n'
+                 'int main(void) {\n'
+                 '  int rc = bv_colsum(NULL, 1, NULL, 4, 7, 7, NULL);   /* 7 columns: rejected before any launch */\n'
+                 '  printf("%d %d %s\\n", bv_version(), rc, bv_last_error_string());\n'
+                 '  return 0;\n}\n')
+  libdir = os.path.dirname(os.path.abspath(L.LIB_PATH))
+  exe = tmp_path / "main"
+  subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                  "-L", libdir, "-lbv_b200", f"-Wl,-rpath,{libdir}"], check=True)
+  out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 2)
+  assert out[0] == "100" and int(out[1]) < 0 and len(out[2].strip()) > 0
