@@ -145,12 +145,15 @@ int bv_patchify_u8(const uint8_t* image, void* patches, int64_t n, int32_t H, in
 /* out[b,l,:] = table[ids[b,l],:] + pos[l,:] (text_transformer.py:63-70); pos may be NULL */
 int bv_embed_fwd(const int32_t* ids, const float* table, const float* pos, void* out,
                  int out_dtype, int64_t n, int32_t L, int32_t d, int32_t vocab, void* stream);
-/* dtable[ids] += dy (atomics), dpos[l] += sum_b dy; either may be NULL */
+/* backward of the embedding lookup + position embedding (text_transformer.py:63-70):
+   dtable[ids] += dy (atomics), dpos[l] += sum_b dy; either may be NULL */
 int bv_embed_bwd(const int32_t* ids, const void* dy, int dy_dtype, float* dtable, float* dpos,
                  int64_t n, int32_t L, int32_t d, int32_t vocab, void* stream);
-/* out[c] += sum_r x[r,c] : bias gradients */
+/* out[c] += sum_r x[r,c] : the bias gradients of flax Dense / DenseGeneral (models/vit.py:72-77,95) and
+   the batch sums behind the pos_embedding / cls gradients (models/vit.py:219-225) */
 int bv_colsum(const void* x, int x_dtype, float* out, int64_t rows, int64_t cols, int64_t ld,
               void* stream);
+/* dtype conversion fp32 <-> bf16: the `dtype_mm` casts of the reference's Dense layers (models/vit.py:61,72-78) */
 int bv_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 /* z = x / (||x||_2 + eps) (two_towers.py:60-61,73-74) */
 int bv_l2norm_fwd(const void* x, int x_dtype, float* z, float* norm, int64_t n, int32_t d,
@@ -164,7 +167,7 @@ int bv_pool_fwd(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, int
 int bv_pool_bwd(const void* dy, int dy_dtype, void* dx, int dx_dtype, int64_t n, int32_t N,
                 int32_t d, int32_t mode, int32_t tok, void* stream);
 /* gradient of the mode-2 pool: dy[n,d] goes to the positions of x[n,N,d] holding the column maximum,
-   split evenly between ties (the jnp.max differentiation rule) */
+   split evenly between ties (the jnp.max differentiation rule; text_transformer.py:89-90) */
 int bv_pool_max_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, void* dx, int dx_dtype,
                     int64_t n, int32_t N, int32_t d, void* stream);
 /* y[r,:] = x[0,:] (+ row[:]) for r < rows : broadcast one row (MAP probe, models/vit.py:174) */
@@ -181,7 +184,8 @@ int bv_axpby(const void* x, const void* y, void* out, int dtype, float a, float 
 /* cls token (models/vit.py:223-225): out[b,0,:] = cls, out[b,1+t,:] = x[b,t,:]  (bf16, cls fp32) */
 int bv_concat_cls(const void* x, const float* cls, void* out, int64_t n, int32_t N0, int32_t d,
                   void* stream);
-/* out[b,t,:] = x[b,1+t,:] : the patch rows of a [n,N0+1,d] tensor (backward of the concat) */
+/* out[b,t,:] = x[b,1+t,:] : the patch rows of a [n,N0+1,d] tensor (backward of the concat of
+   models/vit.py:223-225; also `encoded[:, 1:]` of models/vit.py:251) */
 int bv_drop_cls(const void* x, void* out, int64_t n, int32_t N0, int32_t d, void* stream);
 /* bf16 [n,N,d] -> [n,d,round_up(N,8)] (zero pad): Mixer token mixing, mlp_mixer.py:49-51 */
 int bv_transpose_tokens(const void* x, void* y, int64_t n, int32_t N, int32_t d, void* stream);
@@ -245,6 +249,8 @@ typedef struct bv_adam_args {
   float* upd_sq; float* param_sq;
 } bv_adam_args;
 int bv_adam_step(const bv_adam_args* args, void* stream);
+/* out[0] += sum x^2 : optax.global_norm of the gradients / updates / params (optax.py:100-105
+   `clip_by_global_norm`; trainers/proj/image_text/siglip.py:316-321 `l2_grads`, `l2_params`, `l2_updates`) */
 int bv_sumsq(const float* x, float* out, int64_t n, void* stream);
 /* The same chain with optax.scale(step_size) as the inner transform (plain SGD; what the reference's
  * optimizer known-answer tests drive, optax_test.py:103-299): p += -(lr_eff * g' + wd_eff * p) with
