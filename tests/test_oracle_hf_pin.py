@@ -34,7 +34,7 @@ def _tree(seed):
   return tree
 
 
-def _hf_state(tree):
+def _hf_state(tree, W=W, DEPTH=DEPTH):
   """The oracle's (= the reference's) parameter tree in transformers' SiglipModel layout."""
   t = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in tree.items()}
   sd = {}
@@ -86,22 +86,27 @@ def _hf_state(tree):
   return {k: v.contiguous() for k, v in sd.items()}
 
 
-@pytest.fixture(scope="module")
-def pair():
+def _hf_model(tree, width, depth, mlp, heads, res, patch, vocab, length, out):
   from transformers import SiglipConfig, SiglipModel
-  tree = _tree(0)
-  common_kw = dict(hidden_size=W, intermediate_size=MLP, num_hidden_layers=DEPTH, num_attention_heads=HEADS,
+  common_kw = dict(hidden_size=width, intermediate_size=mlp, num_hidden_layers=depth, num_attention_heads=heads,
                    layer_norm_eps=1e-6, hidden_act="gelu_pytorch_tanh", attention_dropout=0.0)
-  cfg = SiglipConfig(vision_config=dict(common_kw, image_size=RES, patch_size=PATCH, num_channels=3),
-                     text_config=dict(common_kw, vocab_size=VOCAB, max_position_embeddings=LEN, projection_size=OUT))
+  cfg = SiglipConfig(vision_config=dict(common_kw, image_size=res, patch_size=patch, num_channels=3),
+                     text_config=dict(common_kw, vocab_size=vocab, max_position_embeddings=length, projection_size=out))
   cfg._attn_implementation = "eager"
   hf = SiglipModel(cfg).double().eval()
-  state = _hf_state(tree)
+  state = _hf_state(tree, width, depth)
   own = hf.state_dict()
   assert set(state) == set(k for k in own if "position_ids" not in k), set(state) ^ set(own)
   for k, v in state.items():
     assert tuple(v.shape) == tuple(own[k].shape), (k, v.shape, own[k].shape)
   hf.load_state_dict(state, strict=False)
+  return hf
+
+
+@pytest.fixture(scope="module")
+def pair():
+  tree = _tree(0)
+  hf = _hf_model(tree, W, DEPTH, MLP, HEADS, RES, PATCH, VOCAB, LEN, OUT)
   rng = np.random.default_rng(7)
   image = torch.from_numpy(rng.uniform(-1, 1, size=(4, RES, RES, 3))).double()
   text = torch.from_numpy(rng.integers(0, VOCAB, size=(4, LEN)))
@@ -158,6 +163,47 @@ def test_oracle_gradients_match_transformers_siglip(pair):
     mine = p64[name].grad
     scale = float(ref.abs().max()) + 1e-30
     assert float((mine - ref).abs().max()) <= 1e-6 * scale + 1e-12, name
+
+
+def test_committed_golden_vectors_equal_transformers_outputs():
+  """tests/golden/siglip_tiny.npz is what the GPU parity tests (tests/test_model_gpu.py) compare the CUDA path
+  with.  It was written by the oracle (tests/golden/make_golden.py); here its parameters and inputs go
+  through transformers' SiglipModel and must reproduce the file's float32-mode embeddings, loss and every
+  stored gradient -- which ties the GPU tests' reference values to an implementation other than the oracle."""
+  import os
+  import common
+  z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "siglip_tiny.npz"))
+  tree = {k[len("param:"):]: z[k] for k in z.files if k.startswith("param:")}
+  kw = common.TINY
+  hf = _hf_model(tree, kw["image"]["width"], kw["image"]["depth"], kw["image"]["mlp_dim"], kw["image"]["num_heads"],
+                 common.TINY_IMAGE_SHAPE[1], kw["image"]["patch_size"][0], kw["text"]["vocab_size"],
+                 common.TINY_TEXT_SHAPE[1], kw["out_dim"][1])
+  image = torch.from_numpy(z["image"]).double().permute(0, 3, 1, 2)
+  out = hf(input_ids=torch.from_numpy(z["text"]).long(), pixel_values=image, return_loss=True)
+  assert float((out.image_embeds.detach() - torch.from_numpy(z["float32:zimg"])).abs().max()) < 1e-7
+  assert float((out.text_embeds.detach() - torch.from_numpy(z["float32:ztxt"])).abs().max()) < 1e-7
+  assert float(out.loss) == pytest.approx(float(z["float32:loss"]), rel=1e-7)
+  out.loss.backward()
+  g = dict(hf.named_parameters())
+  w = kw["image"]["width"]
+  checks = {
+      "img/pos_embedding": g["vision_model.embeddings.position_embedding.weight"].grad[None],
+      "img/embedding/bias": g["vision_model.embeddings.patch_embedding.bias"].grad,
+      "img/Transformer/encoderblock_0/MlpBlock_0/Dense_0/kernel": g["vision_model.encoder.layers.0.mlp.fc1.weight"].grad.T,
+      "img/Transformer/encoderblock_1/MultiHeadDotProductAttention_0/out/kernel":
+          g["vision_model.encoder.layers.1.self_attn.out_proj.weight"].grad.T.reshape(1, w, w),
+      "img/MAPHead_0/probe": g["vision_model.head.probe"].grad,
+      "img/MAPHead_0/MlpBlock_0/Dense_1/kernel": g["vision_model.head.mlp.fc2.weight"].grad.T,
+      "txt/Embed_0/embedding": g["text_model.embeddings.token_embedding.weight"].grad,
+      "txt/Encoder_0/encoderblock_0/MultiHeadDotProductAttention_0/query/kernel":
+          g["text_model.encoder.layers.0.self_attn.q_proj.weight"].grad.T.reshape(w, 1, w),
+      "txt/Encoder_0/encoder_norm/scale": g["text_model.final_layer_norm.weight"].grad,
+      "txt/head/bias": g["text_model.head.bias"].grad,
+      "t": g["logit_scale"].grad, "b": g["logit_bias"].grad,
+  }
+  for name, ref in checks.items():
+    gold = torch.from_numpy(z["float32:grad:" + name]).double()
+    assert float((gold - ref).abs().max()) <= 1e-6 * float(ref.abs().max()) + 1e-12, name
 
 
 # ---------------------------------------------------------------------------------------------------
