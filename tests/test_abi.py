@@ -101,3 +101,34 @@ def test_header_is_plain_c_and_a_c_program_links(tmp_path):
                   "-L", libdir, "-lbv_b200", f"-Wl,-rpath,{libdir}"], check=True)
   out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(None, 2)
   assert out[0] == "100" and int(out[1]) < 0 and len(out[2].strip()) > 0
+
+
+def test_bench_refuses_to_run_the_product_arm_without_a_gpu():
+  """No CPU fallback: the product arm of bench.py exits non-zero on a box without a GPU instead of timing
+  something else (the reference arm is the only thing that may run on the host cores)."""
+  import subprocess
+  import sys
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("a GPU is present")
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1",
+                      "--no-cpu-baseline", "--no-gpu-baseline"], capture_output=True, text=True, timeout=600)
+  assert r.returncode != 0 and r.stdout.strip() == "" and "needs a GPU" in r.stderr
+
+
+def test_reference_arm_prints_the_contract_line():
+  """`bench.py --impl reference`: the oracle port on the host cores, one JSON line with the same metric /
+  unit / config keys as the product arm plus impl, cpu_baseline and an e2e block with zero copies."""
+  import json
+  import subprocess
+  import sys
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                      "--warmup", "1"], capture_output=True, text=True, timeout=900)
+  assert r.returncode == 0, r.stderr[-2000:]
+  line = json.loads(r.stdout.strip().splitlines()[-1])
+  assert line["impl"] == "reference" and line["metric"] == "siglip_vit_b16_pairs_per_sec" and line["unit"] == "pairs/s"
+  assert line["higher_is_better"] is True and line["steps"] == 1 and line["value"] > 0
+  assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+  assert line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+  assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+  assert "workload" in line["config"] and "model" not in line["config"]
